@@ -1,0 +1,664 @@
+// api.cu -- implementation of the C ABI declared in include/dsrt.h.
+//
+// This is the only layer a host program talks to.  It owns the context (one GPU, one
+// stream), the scene (wide BVH + records + materials), the frame work memory (ray queues,
+// path state, accumulation buffer) and orchestrates the wavefront launches of render.cu.
+// There is deliberately no CPU code path here: every entry that computes needs the device.
+#include "dsrt.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bvh8.cuh"
+#include "bvh_build.h"
+#include "render.cuh"
+
+using namespace dsrt;
+
+namespace {
+
+char g_create_error[512] = "";
+
+constexpr int kMaxEvents = 8192;
+
+}  // namespace
+
+struct dsrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = "";
+
+    // scene
+    bool have_scene = false;
+    Bvh8 bvh;
+    float4* d_mats = nullptr;
+    int nmats = 0;
+    DsrtTextureHeader* d_tex = nullptr;
+    float* d_pool = nullptr;
+    int ntex = 0, pool_floats = 0;
+    DsrtSceneStats sstats{};
+
+    // frame
+    int W = 0, H = 0;
+    float* accum = nullptr;
+    uint32_t* rng_pix = nullptr;
+    unsigned char* d_rgb = nullptr;
+    int lcg_next_sample = -1;
+
+    size_t cap_paths = 0;
+    float4 *rq_o[2] = {nullptr, nullptr}, *rq_d[2] = {nullptr, nullptr};
+    float4 *hits = nullptr, *st_a = nullptr, *st_b = nullptr, *sq_o = nullptr, *sq_l = nullptr;
+    uint32_t* counters = nullptr;
+    unsigned long long* stats = nullptr;
+    uint32_t* h_pinned = nullptr;      // small pinned scratch for counter read-backs
+
+    LaunchDims dims;
+    DsrtFrameStats fstats{};
+    int stage_timing = 0;
+    int spb_override = 0;
+    cudaEvent_t ev_frame[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+
+    // scratch for the trace hooks
+    float4* t_rays = nullptr;
+    float4* t_hits = nullptr;
+    uint8_t* t_occ = nullptr;
+    size_t t_cap = 0;
+};
+
+namespace {
+
+int fail(dsrt_ctx* c, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(ctx, DSRT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+void free_scene(dsrt_ctx* c) {
+    free_bvh8(c->bvh);
+    cudaFree(c->d_mats); c->d_mats = nullptr;
+    cudaFree(c->d_tex); c->d_tex = nullptr;
+    cudaFree(c->d_pool); c->d_pool = nullptr;
+    c->nmats = c->ntex = c->pool_floats = 0;
+    c->have_scene = false;
+}
+
+void free_work(dsrt_ctx* c) {
+    for (int k = 0; k < 2; ++k) { cudaFree(c->rq_o[k]); cudaFree(c->rq_d[k]); c->rq_o[k] = c->rq_d[k] = nullptr; }
+    cudaFree(c->hits); cudaFree(c->st_a); cudaFree(c->st_b); cudaFree(c->sq_o); cudaFree(c->sq_l);
+    c->hits = c->st_a = c->st_b = c->sq_o = c->sq_l = nullptr;
+    c->cap_paths = 0;
+}
+
+int ensure_work(dsrt_ctx* ctx, size_t paths) {
+    if (paths <= ctx->cap_paths) return DSRT_OK;
+    free_work(ctx);
+    const size_t b = paths * sizeof(float4);
+    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&ctx->rq_o[k], b)); CK(cudaMalloc(&ctx->rq_d[k], b)); }
+    CK(cudaMalloc(&ctx->hits, b));
+    CK(cudaMalloc(&ctx->st_a, b));
+    CK(cudaMalloc(&ctx->st_b, b));
+    CK(cudaMalloc(&ctx->sq_o, b));
+    CK(cudaMalloc(&ctx->sq_l, b));
+    ctx->cap_paths = paths;
+    return DSRT_OK;
+}
+
+int ensure_image(dsrt_ctx* ctx, int W, int H, bool* fresh) {
+    *fresh = false;
+    if (ctx->accum && ctx->W == W && ctx->H == H) return DSRT_OK;
+    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb);
+    ctx->accum = nullptr; ctx->rng_pix = nullptr; ctx->d_rgb = nullptr;
+    const size_t px = (size_t)W * H;
+    CK(cudaMalloc(&ctx->accum, px * 3 * sizeof(float)));
+    CK(cudaMalloc(&ctx->rng_pix, px * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_rgb, px * 3));
+    ctx->W = W; ctx->H = H;
+    ctx->lcg_next_sample = -1;
+    *fresh = true;
+    return DSRT_OK;
+}
+
+int ensure_trace_scratch(dsrt_ctx* ctx, size_t n) {
+    if (n <= ctx->t_cap) return DSRT_OK;
+    cudaFree(ctx->t_rays); cudaFree(ctx->t_hits); cudaFree(ctx->t_occ);
+    ctx->t_rays = nullptr; ctx->t_hits = nullptr; ctx->t_occ = nullptr; ctx->t_cap = 0;
+    CK(cudaMalloc(&ctx->t_rays, n * 2 * sizeof(float4)));
+    CK(cudaMalloc(&ctx->t_hits, n * sizeof(float4)));
+    CK(cudaMalloc(&ctx->t_occ, n));
+    ctx->t_cap = n;
+    return DSRT_OK;
+}
+
+// normalise(-sun_dir) with the device's operation order (exact_math.cuh: vdot, vnorm_ref).
+void host_ldir(const float s[3], float out[3]) {
+    const float x = -s[0], y = -s[1], z = -s[2];
+    const float len2 = std::fmaf(z, z, std::fmaf(x, x, y * y));
+    const float L = std::sqrt(len2);
+    if (L <= 0.0f) { out[0] = out[1] = out[2] = 0.0f; return; }
+    const float inv = 1.0f / L;
+    out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+}
+
+cudaEvent_t pool_event(dsrt_ctx* c, size_t i) {
+    while (c->ev_pool.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[i];
+}
+
+}  // namespace
+
+extern "C" const char* dsrt_version(void) { return "dsrt-b200 0.1 sm_100a"; }
+
+extern "C" const char* dsrt_last_error(const dsrt_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+extern "C" int dsrt_create(dsrt_ctx** out, int device) {
+    dsrt_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, DSRT_EINVAL, "dsrt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, DSRT_ECUDA, "no usable CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, DSRT_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, DSRT_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    ctx = new (std::nothrow) dsrt_ctx();
+    if (!ctx) return fail(nullptr, DSRT_ENOMEM, "out of host memory");
+    ctx->device = device;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&ctx->counters, sizeof(uint32_t) * C_COUNT) == cudaSuccess &&
+              cudaMalloc(&ctx->stats, sizeof(unsigned long long) * S_COUNT) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_frame[0]) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_frame[1]) == cudaSuccess;
+    if (!ok) {
+        fail(nullptr, DSRT_ECUDA, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+        dsrt_destroy(ctx);
+        return DSRT_ECUDA;
+    }
+    launch_dims(&ctx->dims, device);
+    *out = ctx;
+    return DSRT_OK;
+}
+
+extern "C" void dsrt_destroy(dsrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    free_work(ctx);
+    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb);
+    cudaFree(ctx->counters); cudaFree(ctx->stats);
+    cudaFree(ctx->t_rays); cudaFree(ctx->t_hits); cudaFree(ctx->t_occ);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) if (ctx->ev_frame[k]) cudaEventDestroy(ctx->ev_frame[k]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void* dsrt_stream(dsrt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+namespace {
+
+// Common tail of the two upload entry points.  `tris`/`mats`/`textures`/`pool` are host
+// pointers when from_device is false and device pointers (on ctx's GPU) when it is true.
+int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris, int ntris,
+                      const DsrtMaterial* mats, int nmats, int nspheres,
+                      const DsrtTextureHeader* textures, int ntextures,
+                      const float* texture_pool, int texture_pool_floats) {
+    if (ntris < 0 || nmats < 0 || (ntris > 0 && !tris) || (nmats > 0 && !mats))
+        return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad triangle/material arguments");
+    if (ntris > 0 && nmats == 0) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: triangles without materials");
+    if (nspheres > 0)
+        return fail(ctx, DSRT_EUNSUPPORTED, "spheres are not built yet (the reference's main() never creates any)");
+    if (ntextures < 0 || (ntextures > 0 && (!textures || !texture_pool || texture_pool_floats <= 0)))
+        return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad texture arguments");
+    if (!from_device)
+        for (int i = 0; i < ntris; ++i)
+            if (tris[i].material_id < 0 || tris[i].material_id >= nmats)
+                return fail(ctx, DSRT_EINVAL, "triangle %d has material_id %d outside [0,%d)", i, tris[i].material_id, nmats);
+    CK(cudaSetDevice(ctx->device));
+    free_scene(ctx);
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+
+    DsrtSceneStats st{};
+    st.num_triangles = ntris;
+    st.max_leaf_tris = kMaxLeafTris;
+
+    if (nmats > 0) {
+        static_assert(sizeof(DsrtMaterial) == 48, "material layout");
+        CK(cudaMalloc(&ctx->d_mats, sizeof(DsrtMaterial) * (size_t)nmats));
+        CK(cudaMemcpyAsync(ctx->d_mats, mats, sizeof(DsrtMaterial) * (size_t)nmats, kind, ctx->stream));
+        ctx->nmats = nmats;
+    }
+    if (ntextures > 0) {
+        CK(cudaMalloc(&ctx->d_tex, sizeof(DsrtTextureHeader) * (size_t)ntextures));
+        CK(cudaMalloc(&ctx->d_pool, sizeof(float) * (size_t)texture_pool_floats));
+        CK(cudaMemcpyAsync(ctx->d_tex, textures, sizeof(DsrtTextureHeader) * (size_t)ntextures, kind, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pool, texture_pool, sizeof(float) * (size_t)texture_pool_floats, kind, ctx->stream));
+        ctx->ntex = ntextures;
+        ctx->pool_floats = texture_pool_floats;
+    }
+    if (ntris > 0) {
+        static_assert(sizeof(DsrtTriangle) == 116, "triangle layout");
+        DsrtTriangle* d_raw = nullptr;
+        if (!from_device) {
+            CK(cudaMalloc(&d_raw, sizeof(DsrtTriangle) * (size_t)ntris));
+            cudaEventRecord(ctx->ev_frame[0], ctx->stream);
+            cudaError_t e = cudaMemcpyAsync(d_raw, tris, sizeof(DsrtTriangle) * (size_t)ntris, cudaMemcpyHostToDevice, ctx->stream);
+            cudaEventRecord(ctx->ev_frame[1], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { cudaFree(d_raw); return fail(ctx, DSRT_ECUDA, "triangle upload: %s", cudaGetErrorString(e)); }
+            cudaEventElapsedTime(&st.upload_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
+        }
+        char msg[256] = "";
+        int rc = build_bvh8(ctx->stream, from_device ? tris : d_raw, ntris, ntextures > 0, &ctx->bvh, msg, sizeof(msg));
+        if (d_raw) cudaFree(d_raw);
+        if (rc != 0) return fail(ctx, DSRT_ECUDA, "BVH build failed: %s", msg);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    st.num_wide_nodes = ctx->bvh.num_nodes;
+    st.num_levels = ctx->bvh.num_levels;
+    st.build_ms = ctx->bvh.build_ms;
+    st.sah_cost = ctx->bvh.sah_cost;
+    for (int a = 0; a < 3; ++a) { st.scene_lo[a] = ctx->bvh.scene_lo[a]; st.scene_hi[a] = ctx->bvh.scene_hi[a]; }
+    st.node_bytes = (uint64_t)ctx->bvh.num_nodes * 80u;
+    st.tri_bytes = (uint64_t)ntris * 48u;
+    ctx->sstats = st;
+    ctx->have_scene = true;
+    return DSRT_OK;
+}
+
+}  // namespace
+
+extern "C" int dsrt_scene_upload(dsrt_ctx* ctx, const DsrtTriangle* tris, int ntris,
+                                 const DsrtMaterial* mats, int nmats,
+                                 const DsrtSphere* spheres, int nspheres,
+                                 const DsrtTextureHeader* textures, int ntextures,
+                                 const float* texture_pool, int texture_pool_floats) {
+    if (!ctx) return DSRT_EINVAL;
+    (void)spheres;
+    return scene_upload_impl(ctx, false, tris, ntris, mats, nmats, nspheres, textures, ntextures,
+                             texture_pool, texture_pool_floats);
+}
+
+extern "C" int dsrt_scene_upload_device(dsrt_ctx* ctx, const DsrtTriangle* tris_device, int ntris,
+                                        const DsrtMaterial* mats_device, int nmats, int nspheres,
+                                        const DsrtTextureHeader* textures_device, int ntextures,
+                                        const float* texture_pool_device, int texture_pool_floats) {
+    if (!ctx) return DSRT_EINVAL;
+    return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, nspheres,
+                             textures_device, ntextures, texture_pool_device, texture_pool_floats);
+}
+
+extern "C" int dsrt_scene_stats(dsrt_ctx* ctx, DsrtSceneStats* out) {
+    if (!ctx || !out) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "no scene uploaded");
+    *out = ctx->sstats;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_scene_download(dsrt_ctx* ctx, void* nodes, size_t node_bytes, void* tri_records, size_t tri_bytes) {
+    if (!ctx) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)ctx->bvh.num_nodes * 80u, tb = (size_t)ctx->bvh.num_tris * 48u;
+    if ((nodes && node_bytes < nb) || (tri_records && tri_bytes < tb))
+        return fail(ctx, DSRT_EINVAL, "dsrt_scene_download: need %zu node bytes and %zu triangle bytes", nb, tb);
+    if (nodes && nb) CK(cudaMemcpyAsync(nodes, ctx->bvh.nodes, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_records && tb) CK(cudaMemcpyAsync(tri_records, ctx->bvh.tri_records, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_set_stage_timing(dsrt_ctx* ctx, int enabled) {
+    if (!ctx) return DSRT_EINVAL;
+    ctx->stage_timing = enabled ? 1 : 0;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples) {
+    if (!ctx || samples < 0) return DSRT_EINVAL;
+    ctx->spb_override = samples;
+    return DSRT_OK;
+}
+
+namespace {
+
+void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
+    fc.nodes = ctx->bvh.nodes;
+    fc.tri_records = ctx->bvh.tri_records;
+    fc.shade_records = ctx->bvh.shade_records;
+    fc.uv_records = ctx->bvh.uv_records;
+    fc.materials = ctx->d_mats;
+    fc.textures = ctx->d_tex;
+    fc.texture_pool = ctx->d_pool;
+    fc.num_nodes = ctx->bvh.num_nodes;
+    fc.num_textures = ctx->ntex;
+    fc.texture_pool_floats = ctx->pool_floats;
+}
+
+void fill_camera(const DsrtCamera* cam, FrameConst& fc) {
+    const DsrtVec3* src[4] = {&cam->origin, &cam->lower_left_corner, &cam->horizontal, &cam->vertical};
+    float* dst[4] = {fc.cam_o, fc.cam_llc, fc.cam_h, fc.cam_v};
+    for (int k = 0; k < 4; ++k) { dst[k][0] = src[k]->x; dst[k][1] = src[k]->y; dst[k][2] = src[k]->z; }
+}
+
+}  // namespace
+
+extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
+                                 const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                                 const DsrtRenderParams* params, uint64_t seed,
+                                 int sample_begin, int sample_end, const int rect[4], int keep_accum) {
+    if (!ctx) return DSRT_EINVAL;
+    if (!camera || !params) return fail(ctx, DSRT_EINVAL, "dsrt_render_frame: camera/params NULL");
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "dsrt_render_frame before dsrt_scene_upload");
+    const int W = params->img_width > 0 ? params->img_width : camera->image_width;
+    const int H = params->img_height > 0 ? params->img_height : camera->image_height;
+    if (W < 2 || H < 2) return fail(ctx, DSRT_EINVAL, "image must be at least 2x2 (got %dx%d)", W, H);
+    const int spp_total = params->samples_per_pixel < 1 ? 1 : params->samples_per_pixel;
+    if (sample_begin < 0 || sample_end < sample_begin || sample_end > spp_total)
+        return fail(ctx, DSRT_EINVAL, "sample range [%d,%d) outside [0,%d)", sample_begin, sample_end, spp_total);
+    int x0 = 0, y0 = 0, x1 = W, y1 = H;
+    if (rect) { x0 = rect[0]; y0 = rect[1]; x1 = rect[2]; y1 = rect[3]; }
+    if (x0 < 0 || y0 < 0 || x1 > W || y1 > H || x1 <= x0 || y1 <= y0)
+        return fail(ctx, DSRT_EINVAL, "bad rectangle [%d,%d)x[%d,%d) for %dx%d", x0, x1, y0, y1, W, H);
+    if (sun_enabled && (!sun_dir || !sun_radiance)) return fail(ctx, DSRT_EINVAL, "sun enabled but sun_dir/sun_radiance NULL");
+    const int rng_mode = params->rng_mode;
+    if (rng_mode != DSRT_RNG_PHILOX && rng_mode != DSRT_RNG_REF_LCG)
+        return fail(ctx, DSRT_EINVAL, "unknown rng_mode %d", rng_mode);
+
+    CK(cudaSetDevice(ctx->device));
+    bool fresh = false;
+    int rc = ensure_image(ctx, W, H, &fresh);
+    if (rc) return rc;
+    if (fresh || (!keep_accum && sample_begin == 0))
+        CK(cudaMemsetAsync(ctx->accum, 0, (size_t)W * H * 3 * sizeof(float), ctx->stream));
+
+    const bool full_rect = (x0 == 0 && y0 == 0 && x1 == W && y1 == H);
+    if (rng_mode == DSRT_RNG_REF_LCG) {
+        // The replay keeps one generator per pixel that runs through the samples in order.
+        if (sample_begin == 0) {
+            launch_lcg_seed(ctx->rng_pix, W, H, (uint32_t)(seed & 0xFFFFFFFFu), ctx->stream);
+        } else if (sample_begin != ctx->lcg_next_sample || !full_rect) {
+            return fail(ctx, DSRT_EINVAL, "LCG replay renders samples in order from 0 (next expected %d, got %d)",
+                        ctx->lcg_next_sample, sample_begin);
+        }
+        ctx->lcg_next_sample = full_rect ? sample_end : -1;
+    }
+
+    FrameConst fc;
+    memset(&fc, 0, sizeof(fc));
+    fill_scene_consts(ctx, fc);
+    fill_camera(camera, fc);
+    fc.W = W; fc.H = H;
+    fc.x0 = x0; fc.y0 = y0; fc.rw = x1 - x0; fc.rh = y1 - y0;
+    fc.tiles_x = (fc.rw + 7) / 8;
+    const int tiles_y = (fc.rh + 3) / 4;
+    fc.slots_per_sample = fc.tiles_x * tiles_y * 32;
+    fc.spp_total = spp_total;
+    fc.max_depth = params->max_depth > 0 ? params->max_depth : 12;
+    fc.rng_mode = rng_mode;
+    fc.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
+    fc.seed_hi = (uint32_t)(seed >> 32);
+    fc.sun_enabled = sun_enabled ? 1 : 0;
+    if (sun_enabled) {
+        host_ldir(sun_dir, fc.ldir);
+        for (int a = 0; a < 3; ++a) fc.sun_rad[a] = sun_radiance[a];
+    }
+
+    // samples of a pixel in flight together
+    int spb = 1;
+    const int nsamples = sample_end - sample_begin;
+    if (rng_mode == DSRT_RNG_PHILOX) {
+        if (ctx->spb_override > 0) spb = ctx->spb_override;
+        else {
+            const long long target = 8ll << 20;   // ~8M paths per batch
+            spb = (int)std::max(1ll, std::min(64ll, target / std::max(1, fc.slots_per_sample)));
+        }
+        spb = std::max(1, std::min(spb, std::max(1, nsamples)));
+    }
+    rc = ensure_work(ctx, (size_t)fc.slots_per_sample * spb);
+    if (rc) return rc;
+    for (int k = 0; k < 2; ++k) { fc.rq_o[k] = ctx->rq_o[k]; fc.rq_d[k] = ctx->rq_d[k]; }
+    fc.hits = ctx->hits; fc.st_a = ctx->st_a; fc.st_b = ctx->st_b; fc.sq_o = ctx->sq_o; fc.sq_l = ctx->sq_l;
+    fc.rng_pix = ctx->rng_pix;
+    fc.accum = ctx->accum;
+    fc.counters = ctx->counters;
+    fc.stats = ctx->stats;
+
+    CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * S_COUNT, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_frame[0], ctx->stream));
+
+    uint32_t launches = 0, batches = 0;
+    size_t nev = 0;                 // events used from the pool (pairs: extend, shadow)
+    std::vector<int> ev_kind;       // 0 = extend, 1 = shadow
+    const bool timing = ctx->stage_timing != 0;
+
+    for (int s0 = sample_begin; s0 < sample_end; s0 += spb) {
+        fc.s0 = s0;
+        fc.spb = std::min(spb, sample_end - s0);
+        launch_batch_begin(fc, ctx->stream);
+        launch_raygen(fc, ctx->dims, ctx->stream);
+        launches += 2;
+        int cur = 0;
+        for (int depth = 0; depth < fc.max_depth; ++depth) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+            if (timing && nev + 4 <= (size_t)kMaxEvents) {
+                e0 = pool_event(ctx, nev); e1 = pool_event(ctx, nev + 1);
+                e2 = pool_event(ctx, nev + 2); e3 = pool_event(ctx, nev + 3);
+            }
+            if (e0) cudaEventRecord(e0, ctx->stream);
+            launch_extend(fc, cur, ctx->dims, ctx->stream);
+            if (e1) cudaEventRecord(e1, ctx->stream);
+            launch_shade(fc, cur, depth, ctx->dims, ctx->stream);
+            if (e2) cudaEventRecord(e2, ctx->stream);
+            launch_shadow(fc, ctx->dims, ctx->stream);
+            if (e3) { cudaEventRecord(e3, ctx->stream); nev += 4; }
+            launch_advance(fc, depth, ctx->stream);
+            launches += 4;
+            cur ^= 1;
+            // Long depth limits (the reference default is 50): stop once the queue is empty.
+            if (depth >= 7 && (depth & 3) == 3 && depth + 1 < fc.max_depth) {
+                CK(cudaMemcpyAsync(ctx->h_pinned, ctx->counters + C_NIN, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                if (ctx->h_pinned[0] == 0u) break;
+            }
+        }
+        launch_resolve(fc, ctx->dims, ctx->stream);
+        ++launches;
+        ++batches;
+    }
+    CK(cudaEventRecord(ctx->ev_frame[1], ctx->stream));
+    CK(cudaGetLastError());
+    unsigned long long hs[S_COUNT];
+    CK(cudaMemcpyAsync(hs, ctx->stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    DsrtFrameStats fs{};
+    fs.primary_rays = hs[S_PRIMARY];
+    fs.bounce_rays = hs[S_BOUNCE];
+    fs.shadow_rays = hs[S_SHADOW];
+    fs.paths = hs[S_PATHS];
+    fs.kernel_launches = launches;
+    fs.batches = batches;
+    cudaEventElapsedTime(&fs.device_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
+    if (timing) {
+        float ext = 0.f, shd = 0.f, shade = 0.f;
+        for (size_t k = 0; k + 3 < nev; k += 4) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+            cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
+            cudaEventElapsedTime(&c, ctx->ev_pool[k + 2], ctx->ev_pool[k + 3]);
+            ext += a; shade += b; shd += c;
+        }
+        fs.extend_ms = ext; fs.shadow_ms = shd; fs.shade_ms = shade;
+    }
+    ctx->fstats = fs;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out) {
+    if (!ctx || !out) return DSRT_EINVAL;
+    *out = ctx->fstats;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_readback_rgb8(dsrt_ctx* ctx, int total_spp, float gamma, unsigned char* dst, size_t bytes) {
+    if (!ctx || !dst) return DSRT_EINVAL;
+    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)ctx->W * ctx->H * 3;
+    if (bytes < need) return fail(ctx, DSRT_EINVAL, "dsrt_readback_rgb8: need %zu bytes, got %zu", need, bytes);
+    CK(cudaSetDevice(ctx->device));
+    const int spp = total_spp < 1 ? 1 : total_spp;
+    const float g = gamma > 0.0f ? gamma : 1.0f;                   // gpu_render.cu:1043
+    launch_tonemap(ctx->accum, ctx->d_rgb, ctx->W, ctx->H, 1.0f / (float)spp, 1.0f / g, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, ctx->d_rgb, need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_readback_accum(dsrt_ctx* ctx, float* dst, size_t bytes) {
+    if (!ctx || !dst) return DSRT_EINVAL;
+    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+    if (bytes < need) return fail(ctx, DSRT_EINVAL, "dsrt_readback_accum: need %zu bytes, got %zu", need, bytes);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, ctx->accum, need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_floats) {
+    if (!ctx || !device_ptr || !num_floats) return DSRT_EINVAL;
+    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    *device_ptr = ctx->accum;
+    *num_floats = (size_t)ctx->W * ctx->H * 3;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_upload_accum(dsrt_ctx* ctx, const float* src, size_t bytes) {
+    if (!ctx || !src) return DSRT_EINVAL;
+    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+    if (bytes != need) return fail(ctx, DSRT_EINVAL, "dsrt_upload_accum: need %zu bytes, got %zu", need, bytes);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->accum, src, need, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSRT_OK;
+}
+
+// ---- parity hooks -------------------------------------------------------------------------
+namespace {
+
+int download_hits(dsrt_ctx* ctx, int n, int32_t* tri, float* t, float* u, float* v) {
+    std::vector<float4> h((size_t)n);
+    CK(cudaMemcpyAsync(h.data(), ctx->t_hits, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        int32_t id;
+        memcpy(&id, &h[i].w, 4);
+        if (tri) tri[i] = id;
+        if (t) t[i] = h[i].x;
+        if (u) u[i] = h[i].y;
+        if (v) v[i] = h[i].z;
+    }
+    return DSRT_OK;
+}
+
+}  // namespace
+
+extern "C" int dsrt_trace_closest_device(dsrt_ctx* ctx, const void* rays_device, int n, void* hits_device) {
+    if (!ctx || n < 0 || (n > 0 && (!rays_device || !hits_device))) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
+    if (n == 0) return DSRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    launch_trace_closest(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
+                         (const float4*)rays_device, n, (float4*)hits_device,
+                         ctx->counters + C_FETCH_EXT, ctx->dims.extend_blocks, ctx->stream);
+    CK(cudaGetLastError());
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_trace_occluded_device(dsrt_ctx* ctx, const void* rays_device, int n, void* occluded_device) {
+    if (!ctx || n < 0 || (n > 0 && (!rays_device || !occluded_device))) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
+    if (n == 0) return DSRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    launch_trace_occluded(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
+                          (const float4*)rays_device, n, (uint8_t*)occluded_device,
+                          ctx->counters + C_FETCH_SHD, ctx->dims.shadow_blocks, ctx->stream);
+    CK(cudaGetLastError());
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_trace_closest(dsrt_ctx* ctx, const float* rays, int n,
+                                  int32_t* tri, float* t, float* u, float* v) {
+    if (!ctx || n < 0 || (n > 0 && !rays)) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
+    if (n == 0) return DSRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_trace_scratch(ctx, (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->t_rays, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = dsrt_trace_closest_device(ctx, ctx->t_rays, n, ctx->t_hits);
+    if (rc) return rc;
+    return download_hits(ctx, n, tri, t, u, v);
+}
+
+extern "C" int dsrt_trace_occluded(dsrt_ctx* ctx, const float* rays, int n, uint8_t* occluded) {
+    if (!ctx || n < 0 || (n > 0 && (!rays || !occluded))) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
+    if (n == 0) return DSRT_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_trace_scratch(ctx, (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->t_rays, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = dsrt_trace_occluded_device(ctx, ctx->t_rays, n, ctx->t_occ);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(occluded, ctx->t_occ, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_first_hits(dsrt_ctx* ctx, const DsrtCamera* camera, int width, int height,
+                               float jx, float jy, int32_t* tri, float* t, float* u, float* v) {
+    if (!ctx || !camera || width < 2 || height < 2) return DSRT_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "dsrt_first_hits before dsrt_scene_upload");
+    CK(cudaSetDevice(ctx->device));
+    const int n = width * height;
+    int rc = ensure_trace_scratch(ctx, (size_t)n);
+    if (rc) return rc;
+    FrameConst fc;
+    memset(&fc, 0, sizeof(fc));
+    fill_camera(camera, fc);
+    fc.W = width; fc.H = height;
+    launch_camera_rays(fc, jx, jy, ctx->t_rays, ctx->stream);
+    CK(cudaGetLastError());
+    rc = dsrt_trace_closest_device(ctx, ctx->t_rays, n, ctx->t_hits);
+    if (rc) return rc;
+    return download_hits(ctx, n, tri, t, u, v);
+}

@@ -1,0 +1,552 @@
+// bvh_build.cu -- GPU construction of the compressed 8-wide BVH.
+//
+// Replaces the reference's per-frame, single-threaded CPU builder
+// (/root/reference/src/gpu_scene_builder.cpp:343-459: recursive median split, leaves <= 4)
+// with a build that runs once per mesh on the device:
+//
+//   1. triangle bounds + scene bounds            (k_tri_bounds)
+//   2. 63-bit Morton codes of box centres        (k_morton)
+//   3. radix sort (cub::DeviceRadixSort)
+//   4. binary radix tree, Karras 2012            (k_hierarchy)
+//   5. bottom-up box refit with atomic flags     (k_refit)
+//   6. top-down collapse, one level per launch:  (k_collapse_level)
+//        greedy surface-area expansion of each binary node into <= 8 children,
+//        subtrees of <= 3 triangles become leaf children,
+//        children are placed in octant-matched slots,
+//        child boxes are quantised to 8 bits against the node box (conservatively),
+//        nodes are emitted breadth first, triangle records in leaf order.
+//
+// The traversal that consumes this layout is in bvh8.cuh.
+#include "bvh_build.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cfloat>
+#include <cstdio>
+
+#include "bvh8.cuh"
+
+namespace dsrt {
+
+namespace {
+
+#define DSRT_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            snprintf(err, err_len, "%s: %s", #call, cudaGetErrorString(e__)); \
+            goto fail;                                                    \
+        }                                                                 \
+    } while (0)
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// bounds[0..2] = min of triangle boxes, [3..5] = max, [6..8] = min of centres, [9..11] = max of
+// centres, all as ordered uints.
+__global__ void k_init_bounds(uint32_t* bounds) {
+    int i = threadIdx.x;
+    if (i < 12) bounds[i] = ((i / 3) & 1) ? 0u : 0xFFFFFFFFu;
+}
+
+__global__ void k_tri_bounds(const DsrtTriangle* __restrict__ tris, int n,
+                             float4* __restrict__ lo, float4* __restrict__ hi,
+                             uint32_t* __restrict__ bounds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float l[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, h[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float c[3] = {0, 0, 0};
+    bool valid = i < n;
+    if (valid) {
+        const float* p = reinterpret_cast<const float*>(tris + i);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v0 = p[a], v1 = p[3 + a], v2 = p[6 + a];
+            l[a] = fminf(fminf(v0, v1), v2);
+            h[a] = fmaxf(fmaxf(v0, v1), v2);
+            c[a] = 0.5f * l[a] + 0.5f * h[a];
+        }
+        lo[i] = make_float4(l[0], l[1], l[2], 0.f);
+        hi[i] = make_float4(h[0], h[1], h[2], 0.f);
+    }
+    // warp reduce, then one atomic per warp per component
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float vl = valid ? l[a] : FLT_MAX, vh = valid ? h[a] : -FLT_MAX;
+        float cl = valid ? c[a] : FLT_MAX, ch = valid ? c[a] : -FLT_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vl = fminf(vl, __shfl_xor_sync(0xffffffffu, vl, o));
+            vh = fmaxf(vh, __shfl_xor_sync(0xffffffffu, vh, o));
+            cl = fminf(cl, __shfl_xor_sync(0xffffffffu, cl, o));
+            ch = fmaxf(ch, __shfl_xor_sync(0xffffffffu, ch, o));
+        }
+        if ((threadIdx.x & 31) == 0 && vl <= vh) {
+            atomicMin(&bounds[a], float_to_ordered(vl));
+            atomicMax(&bounds[3 + a], float_to_ordered(vh));
+            atomicMin(&bounds[6 + a], float_to_ordered(cl));
+            atomicMax(&bounds[9 + a], float_to_ordered(ch));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, int n,
+                         const uint32_t* __restrict__ bounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 l = lo[i], h = hi[i];
+    float c[3] = {0.5f * l.x + 0.5f * h.x, 0.5f * l.y + 0.5f * h.y, 0.5f * l.z + 0.5f * h.z};
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float cmin = ordered_to_float(bounds[6 + a]), cmax = ordered_to_float(bounds[9 + a]);
+        float ext = cmax - cmin;
+        float f = ext > 0.f ? (c[a] - cmin) / ext : 0.f;
+        f = fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+        q[a] = (uint32_t)f;
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- binary radix tree (Karras 2012).  Node ids: inner 0..n-2, leaf k -> (n-1)+k. ----------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n,
+                            int2* __restrict__ children, int* __restrict__ parent,
+                            int2* __restrict__ range) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int left = (first == gamma) ? (n - 1 + gamma) : gamma;
+    int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    children[i] = make_int2(left, right);
+    range[i] = make_int2(first, last);
+    parent[left] = i;
+    parent[right] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// ---- bottom-up refit --------------------------------------------------------------------
+__global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restrict__ tlo,
+                        const float4* __restrict__ thi, int n,
+                        const int2* __restrict__ children, const int* __restrict__ parent,
+                        float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t tri = vals[k];
+    float4 l = tlo[tri], h = thi[tri];
+    int node = n - 1 + k;
+    blo[node] = l;
+    bhi[node] = h;
+    if (n == 1) return;
+    int p = parent[node];
+    while (p >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[p], 1) == 0) return;     // the sibling subtree finishes this node
+        int2 ch = children[p];
+        // volatile-style reads through L2: the sibling's stores were fenced before its atomic
+        float4 l0 = __ldcg(&blo[ch.x]), h0 = __ldcg(&bhi[ch.x]);
+        float4 l1 = __ldcg(&blo[ch.y]), h1 = __ldcg(&bhi[ch.y]);
+        l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+        h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        blo[p] = l;
+        bhi[p] = h;
+        p = parent[p];
+    }
+}
+
+// ---- collapse -------------------------------------------------------------------------------
+struct CollapseArgs {
+    int n;                         // triangles
+    const int2* children;
+    const int2* range;
+    const float4* blo;
+    const float4* bhi;
+    const uint32_t* vals;          // sorted position -> original triangle index
+    const DsrtTriangle* tris;      // raw triangles (device copy)
+    uint4* nodes;                  // out
+    float4* tri_records;           // out
+    uint32_t* counters;            // [0] nodes allocated, [1] triangle records allocated,
+                                   // [2] next-level item count, [3] float bits of SAH accumulator
+    float eps;                     // absolute box padding
+    float inv_root_area;
+};
+
+__device__ __forceinline__ float half_area(float4 l, float4 h) {
+    float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ int subtree_count(const CollapseArgs& A, int node) {
+    if (node >= A.n - 1) return 1;
+    int2 r = A.range[node];
+    return r.y - r.x + 1;
+}
+
+__global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_in, int count_in,
+                                 int2* __restrict__ items_out) {
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= count_in) return;
+    const int bnode = items_in[it].x;
+    const int wnode = items_in[it].y;
+    const int n = A.n;
+
+    int ch[8];
+    int nch;
+    if (subtree_count(A, bnode) <= kMaxLeafTris) {     // whole scene fits one leaf (n <= 3)
+        ch[0] = bnode; nch = 1;
+    } else {
+        int2 c = A.children[bnode];
+        ch[0] = c.x; ch[1] = c.y; nch = 2;
+        while (nch < 8) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int k = 0; k < nch; ++k) {
+                int c2 = ch[k];
+                if (subtree_count(A, c2) <= kMaxLeafTris) continue;
+                float a = half_area(A.blo[c2], A.bhi[c2]);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+            if (best < 0) break;
+            int2 cc = A.children[ch[best]];
+            ch[best] = cc.x;
+            ch[nch++] = cc.y;
+        }
+    }
+
+    const float4 nlo = A.blo[bnode], nhi = A.bhi[bnode];
+    const float eps = A.eps;
+    const float px = nlo.x - eps, py = nlo.y - eps, pz = nlo.z - eps;
+    const float cx = 0.5f * (nlo.x + nhi.x), cy = 0.5f * (nlo.y + nhi.y), cz = 0.5f * (nlo.z + nhi.z);
+
+    // ---- octant-matched slot assignment (greedy on the 8x8 cost table)
+    float4 clo[8], chi[8];
+    float ox[8], oy[8], oz[8];
+    for (int k = 0; k < nch; ++k) {
+        clo[k] = A.blo[ch[k]]; chi[k] = A.bhi[ch[k]];
+        ox[k] = 0.5f * (clo[k].x + chi[k].x) - cx;
+        oy[k] = 0.5f * (clo[k].y + chi[k].y) - cy;
+        oz[k] = 0.5f * (clo[k].z + chi[k].z) - cz;
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    uint32_t child_done = 0, slot_done = 0;
+    for (int round = 0; round < nch; ++round) {
+        float best = -FLT_MAX;
+        int bc = -1, bs = -1;
+        for (int k = 0; k < nch; ++k) {
+            if (child_done & (1u << k)) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (slot_done & (1u << s)) continue;
+                float cost = ((s & 1) ? ox[k] : -ox[k]) + ((s & 2) ? oy[k] : -oy[k]) + ((s & 4) ? oz[k] : -oz[k]);
+                if (cost > best) { best = cost; bc = k; bs = s; }
+            }
+        }
+        slot_child[bs] = bc;
+        child_done |= 1u << bc;
+        slot_done |= 1u << bs;
+    }
+
+    // ---- classify, count, allocate
+    uint32_t imask = 0;
+    int n_inner = 0, n_tris = 0;
+    for (int s = 0; s < 8; ++s) {
+        int k = slot_child[s];
+        if (k < 0) continue;
+        int cnt = subtree_count(A, ch[k]);
+        if (cnt <= kMaxLeafTris) n_tris += cnt;
+        else { imask |= 1u << s; ++n_inner; }
+    }
+    uint32_t child_base = 0, tri_base = 0, item_base = 0;
+    if (n_inner) {
+        child_base = atomicAdd(&A.counters[0], (uint32_t)n_inner);
+        item_base = atomicAdd(&A.counters[2], (uint32_t)n_inner);
+    }
+    if (n_tris) tri_base = atomicAdd(&A.counters[1], (uint32_t)n_tris);
+
+    // ---- quantisation grid
+    int e[3];
+    float scale[3];
+    {
+        float ext[3] = {(nhi.x + eps) - px, (nhi.y + eps) - py, (nhi.z + eps) - pz};
+        for (int a = 0; a < 3; ++a) {
+            int ee;
+            frexpf(ext[a] / 255.0f, &ee);          // 2^ee > ext/255
+            if (ee < -125) ee = -125;
+            while (ldexpf(255.0f, ee) < ext[a]) ++ee;
+            e[a] = ee;
+            scale[a] = ldexpf(1.0f, ee);
+        }
+    }
+    const float p3[3] = {px, py, pz};
+
+    uint32_t meta[8];
+    uint32_t qlo[3][8], qhi[3][8];
+    int rank = 0, tri_off = 0;
+    float sah = half_area(nlo, nhi) * (float)nch * 0.5f;    // cost of testing this node's boxes
+    for (int s = 0; s < 8; ++s) {
+        int k = slot_child[s];
+        if (k < 0) {
+            meta[s] = 0;
+            for (int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }
+            continue;
+        }
+        const float l3[3] = {clo[k].x, clo[k].y, clo[k].z};
+        const float h3[3] = {chi[k].x, chi[k].y, chi[k].z};
+        for (int a = 0; a < 3; ++a) {
+            float fl = floorf((l3[a] - eps - p3[a]) / scale[a]);
+            int ql = (int)fminf(fmaxf(fl, 0.f), 255.f);
+            while (ql > 0 && fmaf((float)ql, scale[a], p3[a]) > l3[a] - 0.5f * eps) --ql;
+            float fh = ceilf((h3[a] + eps - p3[a]) / scale[a]);
+            int qh = (int)fminf(fmaxf(fh, 0.f), 255.f);
+            while (qh < 255 && fmaf((float)qh, scale[a], p3[a]) < h3[a] + 0.5f * eps) ++qh;
+            qlo[a][s] = (uint32_t)ql;
+            qhi[a][s] = (uint32_t)qh;
+        }
+        int node_c = ch[k];
+        int cnt = subtree_count(A, node_c);
+        if (cnt <= kMaxLeafTris) {
+            int first = node_c >= n - 1 ? node_c - (n - 1) : A.range[node_c].x;
+            for (int j = 0; j < cnt; ++j) {
+                uint32_t tri = A.vals[first + j];
+                const float* tp = reinterpret_cast<const float*>(A.tris + tri);
+                float v0x = tp[0], v0y = tp[1], v0z = tp[2];
+                float4* rec = A.tri_records + (size_t)(tri_base + tri_off + j) * kTriWords;
+                rec[0] = make_float4(v0x, v0y, v0z, __uint_as_float(tri));
+                rec[1] = make_float4(__fsub_rn(tp[3], v0x), __fsub_rn(tp[4], v0y), __fsub_rn(tp[5], v0z), 0.f);
+                rec[2] = make_float4(__fsub_rn(tp[6], v0x), __fsub_rn(tp[7], v0y), __fsub_rn(tp[8], v0z), 0.f);
+            }
+            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_off;
+            tri_off += cnt;
+            sah += half_area(clo[k], chi[k]) * (float)cnt;
+        } else {
+            meta[s] = 0x20u | (24u + (uint32_t)s);
+            items_out[item_base + rank] = make_int2(node_c, (int)(child_base + rank));
+            ++rank;
+        }
+    }
+    atomicAdd(reinterpret_cast<float*>(&A.counters[3]), sah * A.inv_root_area);
+
+    auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+    uint4* np = A.nodes + (size_t)wnode * kNodeWords;
+    np[0] = make_uint4(__float_as_uint(px), __float_as_uint(py), __float_as_uint(pz),
+                       (uint32_t)(e[0] + 127) | ((uint32_t)(e[1] + 127) << 8) |
+                           ((uint32_t)(e[2] + 127) << 16) | (imask << 24));
+    np[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+    np[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    np[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    np[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+}
+
+// ---- per-triangle shading records (indexed by the uploaded triangle index) ---------------
+//   s0: n0.xyz, bits(material_id)   s1: n1.xyz, bits(albedo_tex)   s2: n2.xyz, 0
+//   uv (only when textures exist): uv0.xy, uv1.xy | uv2.xy, 0, 0
+__global__ void k_shade_records(const DsrtTriangle* __restrict__ tris, int n,
+                                float4* __restrict__ shade, float4* __restrict__ uvrec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(tris + i);
+    const int* pi = reinterpret_cast<const int*>(tris + i);
+    shade[(size_t)i * 3 + 0] = make_float4(p[9], p[10], p[11], __int_as_float(pi[27]));
+    shade[(size_t)i * 3 + 1] = make_float4(p[12], p[13], p[14], __int_as_float(pi[28]));
+    shade[(size_t)i * 3 + 2] = make_float4(p[15], p[16], p[17], 0.f);
+    if (uvrec) {
+        uvrec[(size_t)i * 2 + 0] = make_float4(p[18], p[19], p[21], p[22]);
+        uvrec[(size_t)i * 2 + 1] = make_float4(p[24], p[25], 0.f, 0.f);
+    }
+}
+
+}  // namespace
+
+void free_bvh8(Bvh8& b) {
+    if (b.nodes) cudaFree(b.nodes);
+    if (b.tri_records) cudaFree(b.tri_records);
+    if (b.shade_records) cudaFree(b.shade_records);
+    if (b.uv_records) cudaFree(b.uv_records);
+    b = Bvh8();
+}
+
+int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv,
+               Bvh8* out, char* err, size_t err_len) {
+    Bvh8 B;
+    float4 *tlo = nullptr, *thi = nullptr, *blo = nullptr, *bhi = nullptr;
+    uint32_t *bounds = nullptr, *vals = nullptr, *vals_s = nullptr, *counters = nullptr;
+    uint64_t *keys = nullptr, *keys_s = nullptr;
+    int2 *children = nullptr, *range = nullptr, *items[2] = {nullptr, nullptr};
+    int *parent = nullptr, *flags = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const int TB = 256;
+    const int nb = (n + TB - 1) / TB;
+    uint32_t hb[12];
+    uint32_t hc[4];
+    int level_count = 1, levels = 0;
+    size_t max_nodes = 0;
+
+    if (n <= 0) { *out = B; return 0; }
+
+    DSRT_CUDA(cudaEventCreate(&ev0));
+    DSRT_CUDA(cudaEventCreate(&ev1));
+    DSRT_CUDA(cudaEventRecord(ev0, stream));
+
+    DSRT_CUDA(cudaMalloc(&tlo, sizeof(float4) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&thi, sizeof(float4) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&bounds, sizeof(uint32_t) * 12));
+    DSRT_CUDA(cudaMalloc(&keys, sizeof(uint64_t) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&keys_s, sizeof(uint64_t) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&vals_s, sizeof(uint32_t) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&children, sizeof(int2) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&range, sizeof(int2) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&parent, sizeof(int) * (size_t)(2 * n)));
+    DSRT_CUDA(cudaMalloc(&flags, sizeof(int) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&blo, sizeof(float4) * (size_t)(2 * n)));
+    DSRT_CUDA(cudaMalloc(&bhi, sizeof(float4) * (size_t)(2 * n)));
+    DSRT_CUDA(cudaMalloc(&counters, sizeof(uint32_t) * 4));
+    DSRT_CUDA(cudaMalloc(&items[0], sizeof(int2) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&items[1], sizeof(int2) * (size_t)n));
+
+    k_init_bounds<<<1, 32, 0, stream>>>(bounds);
+    k_tri_bounds<<<nb, TB, 0, stream>>>(d_tris, n, tlo, thi, bounds);
+    k_morton<<<nb, TB, 0, stream>>>(tlo, thi, n, bounds, keys, vals);
+    DSRT_CUDA(cudaGetLastError());
+
+    DSRT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_s, vals, vals_s, n, 0, 63, stream));
+    DSRT_CUDA(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+    DSRT_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_s, vals, vals_s, n, 0, 63, stream));
+
+    DSRT_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
+    if (n > 1) k_hierarchy<<<(n - 1 + TB - 1) / TB, TB, 0, stream>>>(keys_s, n, children, parent, range);
+    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, blo, bhi, flags);
+    DSRT_CUDA(cudaGetLastError());
+
+    DSRT_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+    DSRT_CUDA(cudaStreamSynchronize(stream));
+
+    // Output arrays.  A wide node has >= 2 children unless it is the lone root, and every
+    // inner child of a wide node holds >= 4 triangles, so n/2 + 1 nodes always suffice.
+    max_nodes = (size_t)n / 2 + 2;
+    DSRT_CUDA(cudaMalloc(&B.nodes, sizeof(uint4) * kNodeWords * max_nodes));
+    DSRT_CUDA(cudaMalloc(&B.tri_records, sizeof(float4) * kTriWords * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&B.shade_records, sizeof(float4) * 3 * (size_t)n));
+    if (want_uv) DSRT_CUDA(cudaMalloc(&B.uv_records, sizeof(float4) * 2 * (size_t)n));
+    k_shade_records<<<nb, TB, 0, stream>>>(d_tris, n, B.shade_records, B.uv_records);
+
+    {
+        float ext = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            B.scene_lo[a] = ordered_to_float(hb[a]);
+            B.scene_hi[a] = ordered_to_float(hb[3 + a]);
+            ext = fmaxf(ext, B.scene_hi[a] - B.scene_lo[a]);
+            ext = fmaxf(ext, fmaxf(fabsf(B.scene_lo[a]), fabsf(B.scene_hi[a])));
+        }
+        if (!(ext > 0.f)) ext = 1.f;
+        CollapseArgs A;
+        A.n = n; A.children = children; A.range = range; A.blo = blo; A.bhi = bhi;
+        A.vals = vals_s; A.tris = d_tris; A.nodes = B.nodes; A.tri_records = B.tri_records;
+        A.counters = counters;
+        A.eps = ext * (1.0f / 524288.0f);         // 2^-19 of the scene size
+        {
+            float dx = B.scene_hi[0] - B.scene_lo[0], dy = B.scene_hi[1] - B.scene_lo[1], dz = B.scene_hi[2] - B.scene_lo[2];
+            float ra = dx * dy + dy * dz + dz * dx;
+            A.inv_root_area = ra > 0.f ? 1.0f / ra : 0.f;
+        }
+        hc[0] = 1; hc[1] = 0; hc[2] = 0; hc[3] = 0;
+        DSRT_CUDA(cudaMemcpyAsync(counters, hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
+        // binary root: inner node 0, or the single leaf when n == 1
+        int2 root_item = make_int2(n == 1 ? 0 : 0, 0);
+        if (n == 1) root_item.x = 0;               // leaf id n-1+0 == 0
+        DSRT_CUDA(cudaMemcpyAsync(items[0], &root_item, sizeof(int2), cudaMemcpyHostToDevice, stream));
+        int cur = 0;
+        while (level_count > 0) {
+            ++levels;
+            k_collapse_level<<<(level_count + 127) / 128, 128, 0, stream>>>(A, items[cur], level_count, items[cur ^ 1]);
+            DSRT_CUDA(cudaGetLastError());
+            DSRT_CUDA(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+            DSRT_CUDA(cudaStreamSynchronize(stream));
+            level_count = (int)hc[2];
+            uint32_t zero = 0;
+            DSRT_CUDA(cudaMemcpyAsync(counters + 2, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+            cur ^= 1;
+            if (levels > kSmemStack + kLocalStack) {
+                snprintf(err, err_len, "wide BVH deeper than the traversal stack (%d levels)", levels);
+                goto fail;
+            }
+        }
+        B.num_nodes = (int)hc[0];
+        B.num_tris = n;
+        B.num_levels = levels;
+        memcpy(&B.sah_cost, &hc[3], 4);
+        if ((int)hc[1] != n) {
+            snprintf(err, err_len, "collapse emitted %u triangle records for %d triangles", hc[1], n);
+            goto fail;
+        }
+    }
+
+    DSRT_CUDA(cudaEventRecord(ev1, stream));
+    DSRT_CUDA(cudaEventSynchronize(ev1));
+    DSRT_CUDA(cudaEventElapsedTime(&B.build_ms, ev0, ev1));
+
+    cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
+    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
+    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters);
+    cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    *out = B;
+    return 0;
+
+fail:
+    cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
+    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
+    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters);
+    cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    free_bvh8(B);
+    return -1;
+}
+
+}  // namespace dsrt

@@ -1,0 +1,32 @@
+// bvh_build.h -- host interface of the GPU BVH8 builder (bvh_build.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dsrt_types.h"
+
+namespace dsrt {
+
+struct Bvh8 {
+    uint4* nodes = nullptr;          // num_nodes x 5 words (80 B each), breadth-first
+    float4* tri_records = nullptr;   // num_tris x 3 words (48 B each), leaf order
+    float4* shade_records = nullptr; // num_tris x 3 words, indexed by uploaded triangle index
+    float4* uv_records = nullptr;    // num_tris x 2 words, only when textures are present
+    int num_nodes = 0;
+    int num_tris = 0;
+    int num_levels = 0;
+    float build_ms = 0.f;
+    float sah_cost = 0.f;
+    float scene_lo[3] = {0, 0, 0};
+    float scene_hi[3] = {0, 0, 0};
+};
+
+// Builds the wide BVH for `n` triangles already resident on the device in the reference's
+// 116-byte layout.  Returns 0, or -1 with a message in `err`.
+int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv,
+               Bvh8* out, char* err, size_t err_len);
+void free_bvh8(Bvh8& b);
+
+}  // namespace dsrt

@@ -1,0 +1,88 @@
+// render.cuh -- shared declarations of the wavefront path tracer (render.cu) and the C ABI
+// implementation (api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dsrt_types.h"
+
+namespace dsrt {
+
+// Device counters (uint32) -- one cache line, reset per batch; statistics follow as uint64.
+enum {
+    C_NIN = 0,        // rays in the current queue
+    C_NOUT = 1,       // rays pushed to the next queue
+    C_NSHADOW = 2,    // shadow rays pushed this bounce
+    C_FETCH_EXT = 3,  // dynamic work counter of the extend kernel
+    C_FETCH_SHD = 4,  // dynamic work counter of the shadow kernel
+    C_COUNT = 8
+};
+enum { S_PRIMARY = 0, S_BOUNCE = 1, S_SHADOW = 2, S_PATHS = 3, S_COUNT = 4 };
+
+// Everything a frame's kernels need, passed by value as a __grid_constant__ parameter so
+// that every field is a constant-bank read (the reference dereferences a GPUScene* in
+// global memory for each field, gpu_render.cu:981).
+struct FrameConst {
+    // scene
+    const uint4* nodes;
+    const float4* tri_records;
+    const float4* shade_records;
+    const float4* uv_records;
+    const float4* materials;          // DsrtMaterial as 3 x float4
+    const DsrtTextureHeader* textures;
+    const float* texture_pool;
+    int num_nodes, num_textures, texture_pool_floats;
+    // camera (reference GPUCamera fields that the kernel reads)
+    float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
+    int W, H;
+    int x0, y0, rw, rh;               // render rectangle
+    int tiles_x, slots_per_sample;    // 8x4-pixel tiles; slots = tiles*32
+    // estimator
+    int spp_total, max_depth, rng_mode;
+    uint32_t seed_lo, seed_hi;
+    int sun_enabled;
+    float ldir[3];                    // normalise(-sun_dir), computed with the reference's ops
+    float sun_rad[3];
+    // batch
+    int s0, spb;                      // first global sample index and samples in this batch
+    // work memory
+    float4* rq_o[2];                  // ray queue: origin.xyz, bits(path)
+    float4* rq_d[2];                  // ray queue: dir.xyz, unused
+    float4* hits;                     // t,u,v,bits(uploaded triangle index) per queue entry
+    float4* st_a;                     // per path: throughput.xyz, bits(rng state / draw index)
+    float4* st_b;                     // per path: L.xyz (clamped when finished), bits(depth)
+    float4* sq_o;                     // shadow queue: origin.xyz, bits(path | final<<31)
+    float4* sq_l;                     // shadow queue: L if the sun is visible
+    uint32_t* rng_pix;                // LCG replay: per-pixel generator state
+    float* accum;                     // W*H*3 sum of clamped samples, row 0 = bottom
+    uint32_t* counters;               // C_COUNT uint32
+    unsigned long long* stats;        // S_COUNT uint64
+};
+
+struct LaunchDims {
+    int extend_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+};
+
+// Host-callable launchers (all asynchronous on `s`).
+void launch_dims(LaunchDims* d, int device);
+void launch_batch_begin(const FrameConst& fc, cudaStream_t s);
+void launch_raygen(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
+void launch_extend(const FrameConst& fc, int cur, const LaunchDims& d, cudaStream_t s);
+void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
+void launch_shadow(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
+void launch_advance(const FrameConst& fc, int depth, cudaStream_t s);
+void launch_resolve(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
+void launch_tonemap(const float* accum, unsigned char* rgb, int W, int H, float inv_spp, float inv_gamma, cudaStream_t s);
+void launch_lcg_seed(uint32_t* rng_pix, int W, int H, uint32_t seed32, cudaStream_t s);
+
+// Generic traversal over an array of rays {ox,oy,oz,tmin | dx,dy,dz,tmax}.
+void launch_trace_closest(const uint4* nodes, const float4* tri_records, int num_nodes,
+                          const float4* rays, int n, float4* hits, uint32_t* fetch_counter,
+                          int blocks, cudaStream_t s);
+void launch_trace_occluded(const uint4* nodes, const float4* tri_records, int num_nodes,
+                           const float4* rays, int n, uint8_t* occluded, uint32_t* fetch_counter,
+                           int blocks, cudaStream_t s);
+void launch_camera_rays(const FrameConst& fc, float jx, float jy, float4* rays, cudaStream_t s);
+
+}  // namespace dsrt

@@ -1,0 +1,347 @@
+// main.cpp -- the `ray_tracer` command line, drop-in for /root/reference/src/main.cpp.
+//
+// Same flags (--input_txt <file>, --output_dir <dir>, --upscale; unknown flags ignored,
+// main.cpp:194-215), same pose file and fallback pose (:139-173, :272-287), same per-frame
+// banner and skip rule (:319-345), same defaults (800x450, 1000 spp, depth 50, vfov 40,
+// :254-260), same outputs (<out>/frame_%04zu.ppm + .png, :418-426; the output directory is
+// emptied first, :41-50).  What changes is behind the C ABI: the scene is uploaded and its
+// BVH built once, each frame only sets camera + sun, and frames are spread over the GPUs of
+// the node (frame-parallel, no collective) or one frame's samples are sharded across them
+// and summed with a single NCCL reduce.
+//
+// Extra, optional flags (defaults reproduce the reference): --width --height --spp
+// --max_depth --seed --synthetic_tris N --diffuse_only --gpus G --shard frame|sample
+// --frames a:b --rng philox|lcg --no_png --stats_json <file>.
+#include "dsrt.h"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#ifdef DSRT_WITH_NCCL
+#include <cuda_runtime.h>
+#include <nccl.h>
+#endif
+
+namespace fs = std::filesystem;
+
+namespace {
+
+struct Options {
+    std::string pose_file, out_dir = "output", stats_json, shard = "frame", rng = "philox";
+    bool upscale = false, png = true, diffuse_only = false;
+    int width = 800, height = 450, spp = 1000, max_depth = 50;
+    int synthetic_tris = 1000000, gpus = 1, frame_begin = 0, frame_end = -1;
+    float vfov = 40.0f;
+    unsigned long long seed = 1337ULL;        // gpu_scene_builder.cpp:583
+};
+
+void parse_args(int argc, char** argv, Options& o) {
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&](const char* name) -> const char* { return (a == name && i + 1 < argc) ? argv[++i] : nullptr; };
+        if (const char* v = next("--input_txt")) o.pose_file = v;
+        else if (const char* v = next("--output_dir")) o.out_dir = v;
+        else if (a == "--upscale") o.upscale = true;
+        else if (const char* v = next("--width")) o.width = std::atoi(v);
+        else if (const char* v = next("--height")) o.height = std::atoi(v);
+        else if (const char* v = next("--spp")) o.spp = std::atoi(v);
+        else if (const char* v = next("--max_depth")) o.max_depth = std::atoi(v);
+        else if (const char* v = next("--seed")) o.seed = std::strtoull(v, nullptr, 10);
+        else if (const char* v = next("--synthetic_tris")) o.synthetic_tris = std::atoi(v);
+        else if (a == "--diffuse_only") o.diffuse_only = true;
+        else if (const char* v = next("--gpus")) o.gpus = std::atoi(v);
+        else if (const char* v = next("--shard")) o.shard = v;
+        else if (const char* v = next("--rng")) o.rng = v;
+        else if (a == "--no_png") o.png = false;
+        else if (const char* v = next("--stats_json")) o.stats_json = v;
+        else if (const char* v = next("--frames")) {
+            const char* c = std::strchr(v, ':');
+            o.frame_begin = std::atoi(v);
+            o.frame_end = c ? std::atoi(c + 1) : o.frame_begin + 1;
+        }
+        // anything else: ignored, as in the reference
+    }
+}
+
+void prepare_output_dir(const std::string& dir) {
+    if (fs::exists(dir)) {
+        for (auto& entry : fs::directory_iterator(dir)) fs::remove_all(entry.path());
+    } else {
+        fs::create_directories(dir);
+    }
+}
+
+struct FrameJob {
+    size_t index;
+    double pose[9];
+    float cam_in_model[3];
+    float sun_dir[3];
+};
+
+struct FrameResult {
+    double device_ms = 0, rays = 0;
+    bool done = false;
+};
+
+const float kSunRadiance[3] = {100000.0f, 95000.0f, 90000.0f};   // gpu_scene_builder.cpp:598
+
+DsrtRenderParams make_params(const Options& o) {
+    DsrtRenderParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.img_width = o.width; p.img_height = o.height;
+    p.samples_per_pixel = o.spp; p.max_depth = o.max_depth;
+    p.use_bvh = 1;
+    p.rng_mode = o.rng == "lcg" ? DSRT_RNG_REF_LCG : DSRT_RNG_PHILOX;
+    p.gamma = 2.0f; p.exposure = 50.0f;                       // gpu_scene_builder.cpp:579-580
+    return p;
+}
+
+bool save_frame(const Options& o, size_t index, const std::vector<unsigned char>& rgb) {
+    char name[64];
+    std::snprintf(name, sizeof(name), "frame_%04zu.ppm", index);
+    const std::string ppm = o.out_dir + "/" + name;
+    std::snprintf(name, sizeof(name), "frame_%04zu.png", index);
+    const std::string png = o.out_dir + "/" + name;
+    if (dsrt_write_ppm(ppm.c_str(), rgb.data(), o.width, o.height) != DSRT_OK) return false;
+    if (o.png && dsrt_write_png(png.c_str(), rgb.data(), o.width, o.height) != DSRT_OK) return false;
+    return true;
+}
+
+std::mutex g_print;
+
+// One GPU renders the frames jobs[k] with k % stride == offset.
+void frame_worker(int device, const Options& o, const std::vector<DsrtTriangle>& tris,
+                  const std::vector<DsrtMaterial>& mats, const std::vector<FrameJob>& jobs,
+                  int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors) {
+    dsrt_ctx* ctx = nullptr;
+    if (dsrt_create(&ctx, device) != DSRT_OK) {
+        std::lock_guard<std::mutex> l(g_print);
+        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(nullptr));
+        ++errors;
+        return;
+    }
+    if (dsrt_scene_upload(ctx, tris.data(), (int)tris.size(), mats.data(), (int)mats.size(),
+                          nullptr, 0, nullptr, 0, nullptr, 0) != DSRT_OK) {
+        std::lock_guard<std::mutex> l(g_print);
+        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(ctx));
+        ++errors;
+        dsrt_destroy(ctx);
+        return;
+    }
+    {
+        DsrtSceneStats st;
+        dsrt_scene_stats(ctx, &st);
+        std::lock_guard<std::mutex> l(g_print);
+        std::cout << "GPU " << device << " scene build time: " << st.build_ms << " ms (" << st.num_wide_nodes
+                  << " wide nodes, upload " << st.upload_ms << " ms)\n";
+    }
+    const DsrtRenderParams params = make_params(o);
+    std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+    for (size_t k = (size_t)offset; k < jobs.size(); k += (size_t)stride) {
+        const FrameJob& j = jobs[k];
+        DsrtCamera cam;
+        dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
+        int rc = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
+        if (rc == DSRT_OK) rc = dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb.data(), rgb.size());
+        if (rc != DSRT_OK) {
+            std::lock_guard<std::mutex> l(g_print);
+            std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, device, dsrt_last_error(ctx));
+            ++errors;
+            continue;                       // no stale file is renamed into place
+        }
+        DsrtFrameStats fs;
+        dsrt_frame_stats(ctx, &fs);
+        results[k].device_ms = fs.device_ms;
+        results[k].rays = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
+        results[k].done = save_frame(o, j.index, rgb);
+        std::lock_guard<std::mutex> l(g_print);
+        char name[64];
+        std::snprintf(name, sizeof(name), "frame_%04zu.png", j.index);
+        std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << device << ", " << fs.device_ms << " ms, "
+                  << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
+    }
+    dsrt_destroy(ctx);
+}
+
+#ifdef DSRT_WITH_NCCL
+// One frame at a time, its samples split over the GPUs; one ncclReduce(sum) of the float
+// accumulation buffer to GPU 0, which tone-maps and writes the frame.
+int sample_sharded(const Options& o, const std::vector<DsrtTriangle>& tris, const std::vector<DsrtMaterial>& mats,
+                   const std::vector<FrameJob>& jobs, std::vector<FrameResult>& results) {
+    const int G = o.gpus;
+    std::vector<dsrt_ctx*> ctx(G, nullptr);
+    std::vector<ncclComm_t> comm(G);
+    std::vector<int> devs(G);
+    for (int g = 0; g < G; ++g) devs[g] = g;
+    if (ncclCommInitAll(comm.data(), G, devs.data()) != ncclSuccess) { std::fprintf(stderr, "ncclCommInitAll failed\n"); return 1; }
+    int errors = 0;
+    {
+        std::vector<std::thread> th;
+        std::atomic<int> err(0);
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] {
+                if (dsrt_create(&ctx[g], g) != DSRT_OK ||
+                    dsrt_scene_upload(ctx[g], tris.data(), (int)tris.size(), mats.data(), (int)mats.size(),
+                                      nullptr, 0, nullptr, 0, nullptr, 0) != DSRT_OK) {
+                    std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx[g]));
+                    ++err;
+                }
+            });
+        for (auto& t : th) t.join();
+        errors = err;
+    }
+    if (errors) return 1;
+    const DsrtRenderParams params = make_params(o);
+    std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        const FrameJob& j = jobs[k];
+        DsrtCamera cam;
+        dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
+        std::vector<std::thread> th;
+        std::atomic<int> err(0);
+        std::vector<double> ms(G, 0.0), rays(G, 0.0);
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] {
+                // global sample indices stay global: the jitter depends on s/spp (gpu_render.cu:995-996)
+                const int s0 = (int)((long long)o.spp * g / G), s1 = (int)((long long)o.spp * (g + 1) / G);
+                if (dsrt_render_frame(ctx[g], &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, s0, s1, nullptr, 0) != DSRT_OK) { ++err; return; }
+                DsrtFrameStats fs;
+                dsrt_frame_stats(ctx[g], &fs);
+                ms[g] = fs.device_ms;
+                rays[g] = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
+            });
+        for (auto& t : th) t.join();
+        if (err) { std::fprintf(stderr, "frame %zu: render failed\n", j.index); ++errors; continue; }
+        ncclGroupStart();
+        for (int g = 0; g < G; ++g) {
+            void* acc = nullptr; size_t nf = 0;
+            dsrt_accum_device(ctx[g], &acc, &nf);
+            cudaSetDevice(g);
+            ncclReduce(acc, acc, nf, ncclFloat, ncclSum, 0, comm[g], (cudaStream_t)dsrt_stream(ctx[g]));
+        }
+        ncclGroupEnd();
+        for (int g = 0; g < G; ++g) { cudaSetDevice(g); cudaStreamSynchronize((cudaStream_t)dsrt_stream(ctx[g])); }
+        if (dsrt_readback_rgb8(ctx[0], o.spp, params.gamma, rgb.data(), rgb.size()) != DSRT_OK) { ++errors; continue; }
+        double mx = 0, total = 0;
+        for (int g = 0; g < G; ++g) { mx = std::max(mx, ms[g]); total += rays[g]; }
+        results[k].device_ms = mx; results[k].rays = total;
+        results[k].done = save_frame(o, j.index, rgb);
+        std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, " << mx << " ms, "
+                  << total / (mx * 1e3) << " Mrays/s]\n";
+    }
+    for (int g = 0; g < G; ++g) { dsrt_destroy(ctx[g]); ncclCommDestroy(comm[g]); }
+    return errors ? 1 : 0;
+}
+#endif
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    using clk = std::chrono::high_resolution_clock;
+    Options o;
+    parse_args(argc, argv, o);
+    prepare_output_dir(o.out_dir);
+
+    std::cout << "Using input_txt : " << (o.pose_file.empty() ? "(none)" : o.pose_file) << "\n";
+    std::cout << "Using output_dir: " << o.out_dir << "\n";
+    if (o.upscale) std::cout << "--upscale: the Real-ESRGAN post-process is outside this renderer; ignored.\n";
+    const auto total_start = clk::now();
+
+    // The mesh is static in the model frame: generated (or, later, loaded) once.
+    const auto t1 = clk::now();
+    std::vector<DsrtTriangle> tris((size_t)std::max(0, o.synthetic_tris));
+    std::vector<DsrtMaterial> mats(32);
+    const int nm = dsrt_synth_mesh((int)tris.size(), 1337u, o.diffuse_only ? 1 : 0, tris.data(), mats.data(), (int)mats.size());
+    if (nm < 0) { std::fprintf(stderr, "synthetic mesh generation failed\n"); return 1; }
+    mats.resize((size_t)nm);
+    const auto t2 = clk::now();
+    std::cout << "Base ISS + material load time: "
+              << std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count() << " ms ("
+              << tris.size() << " synthetic triangles)\n";
+
+    // Poses, or the reference's single default pose.
+    std::vector<double> poses;
+    int np = 0;
+    if (!o.pose_file.empty()) {
+        np = dsrt_read_pose_file(o.pose_file.c_str(), nullptr, 0);
+        if (np > 0) { poses.resize((size_t)np * 9); dsrt_read_pose_file(o.pose_file.c_str(), poses.data(), np); }
+    }
+    if (np <= 0) {
+        std::cout << "No valid pose file found; using single default pose.\n";
+        const double def[9] = {0.0, 50.0, 200.0, 0.0, -100.0, 0.0, 0.0, 0.0, 0.0};
+        poses.assign(def, def + 9);
+        np = 1;
+    } else {
+        std::cout << "Loaded " << np << " poses.\n";
+    }
+
+    std::vector<FrameJob> jobs;
+    const int fb = std::max(0, o.frame_begin), fe = o.frame_end < 0 ? np : std::min(np, o.frame_end);
+    for (int i = fb; i < fe; ++i) {
+        const double* p = &poses[(size_t)i * 9];
+        FrameJob j;
+        j.index = (size_t)i;
+        std::memcpy(j.pose, p, sizeof(j.pose));
+        double sep = 0;
+        dsrt_pose_to_model_frame(p, j.cam_in_model, j.sun_dir, &sep);
+        std::cout << "\n=== Frame " << i << " ===\n";
+        std::cout << "Camera world: (" << p[0] << ", " << p[1] << ", " << p[2] << ")\n";
+        std::cout << "Model world : (" << p[3] << ", " << p[4] << ", " << p[5] << ")\n";
+        std::cout << "Model yaw/pitch/roll (deg): (" << (float)p[6] << ", " << (float)p[7] << ", " << (float)p[8] << ")\n";
+        std::cout << "  sep(cam, model) = " << sep << " m\n";
+        if (sep < 1.0) {
+            std::cout << "  [!] Camera is inside/too close to ISS mesh. Skipping frame.\n";
+            continue;
+        }
+        std::cout << "  sun_dir_model   = (" << j.sun_dir[0] << ", " << j.sun_dir[1] << ", " << j.sun_dir[2] << ")\n";
+        jobs.push_back(j);
+    }
+
+    std::vector<FrameResult> results(jobs.size());
+    int rc = 0;
+    const int G = std::max(1, o.gpus);
+    if (o.shard == "sample" && G > 1) {
+#ifdef DSRT_WITH_NCCL
+        rc = sample_sharded(o, tris, mats, jobs, results);
+#else
+        std::fprintf(stderr, "--shard sample needs a build with NCCL\n");
+        rc = 1;
+#endif
+    } else {
+        std::atomic<int> errors(0);
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g)
+            th.emplace_back(frame_worker, g, std::cref(o), std::cref(tris), std::cref(mats), std::cref(jobs), g, G,
+                            std::ref(results), std::ref(errors));
+        for (auto& t : th) t.join();
+        rc = errors ? 1 : 0;
+    }
+
+    const auto total_end = clk::now();
+    const double total_s = std::chrono::duration<double>(total_end - total_start).count();
+    double rays = 0, ms = 0;
+    size_t done = 0;
+    for (const auto& r : results) { if (r.done) { ++done; rays += r.rays; ms += r.device_ms; } }
+    std::cout << "\nTotal runtime: " << (long long)total_s << " s\n";
+    if (done) std::cout << "Frames: " << done << ", device time " << ms << " ms, " << rays / (ms * 1e3) << " Mrays/s per GPU-time\n";
+    if (!o.stats_json.empty()) {
+        if (FILE* f = std::fopen(o.stats_json.c_str(), "w")) {
+            std::fprintf(f, "{\"frames\": %zu, \"gpus\": %d, \"shard\": \"%s\", \"total_s\": %.3f, \"device_ms\": %.3f, \"rays\": %.0f}\n",
+                         done, G, o.shard.c_str(), total_s, ms, rays);
+            std::fclose(f);
+        }
+    }
+    std::cout << (o.upscale ? "" : "Upscaling disabled (use --upscale to enable).\n");
+    std::cout << "Done.\n";
+    return rc;
+}

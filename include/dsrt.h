@@ -1,0 +1,165 @@
+/* dsrt.h -- C ABI of the B200 render path (libdsrt.so).
+ *
+ * This is the boundary a reference-side caller binds instead of the reference's three
+ * host->CUDA calls:
+ *
+ *   GPUScene build_gpu_scene(const hittable_list&, const camera&, const vec3& sun_dir_model)
+ *                                            /root/reference/inc/gpu_scene_builder.h:72
+ *                                            /root/reference/src/gpu_scene_builder.cpp:464-601
+ *   extern "C" void gpu_render_scene(const GPUScene&, int width, int height)
+ *                                            /root/reference/src/main.cpp:24-25
+ *                                            /root/reference/src/gpu_render.cu:1037-1108
+ *   void free_gpu_scene(GPUScene&)           /root/reference/inc/gpu_scene_builder.h:73
+ *                                            /root/reference/src/gpu_scene_builder.cpp:603-626
+ *
+ * Conventions: every call returns 0 on success and a negative DSRT_E* code on failure; no
+ * exception crosses the boundary; dsrt_last_error() gives the text.  A ctx owns all of its
+ * device memory and one non-default CUDA stream, lives on one GPU, and is used by one host
+ * thread at a time.  All pointers are plain host pointers unless the name says "device".
+ * There is no CPU fallback: without a usable CUDA device dsrt_create fails.
+ */
+#ifndef DSRT_H
+#define DSRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "dsrt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSRT_OK            0
+#define DSRT_EINVAL       -1   /* bad argument */
+#define DSRT_ECUDA        -2   /* a CUDA runtime call failed */
+#define DSRT_ENOSCENE     -3   /* render/trace before dsrt_scene_upload */
+#define DSRT_EUNSUPPORTED -4   /* feature of GPUScene not built yet (spheres) */
+#define DSRT_EIO          -5   /* file could not be read/written */
+#define DSRT_ENOMEM       -6
+
+typedef struct dsrt_ctx dsrt_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device`.  Replaces nothing in the reference (which uses
+ * the current device and the default stream, gpu_render.cu:1052-1097). */
+int  dsrt_create(dsrt_ctx** out, int device);
+void dsrt_destroy(dsrt_ctx* ctx);
+/* Text of the last error of `ctx`; with ctx == NULL the last dsrt_create failure. */
+const char* dsrt_last_error(const dsrt_ctx* ctx);
+/* The ctx stream as a cudaStream_t, for callers that order their own work after ours. */
+void* dsrt_stream(dsrt_ctx* ctx);
+
+/* ---- scene: replaces build_gpu_scene()'s flatten + CPU BVH + 7 uploads ----------------
+ * Copies the reference-layout arrays to the device and builds, on the GPU, a Morton-sorted
+ * LBVH that is collapsed by surface area into an 8-wide BVH with quantised child boxes
+ * (80-byte nodes) and 48-byte triangle records in leaf order.  Done once per mesh, not per
+ * frame.  Spheres are part of GPUScene but never instantiated by the reference's main();
+ * nspheres > 0 returns DSRT_EUNSUPPORTED. */
+int dsrt_scene_upload(dsrt_ctx* ctx,
+                      const DsrtTriangle* tris, int ntris,
+                      const DsrtMaterial* mats, int nmats,
+                      const DsrtSphere* spheres, int nspheres,
+                      const DsrtTextureHeader* textures, int ntextures,
+                      const float* texture_pool, int texture_pool_floats);
+/* Same, from arrays that already live in the memory of ctx's GPU (what the reference's
+ * GPUScene holds after its own build_gpu_scene): the triangle array is consumed in place,
+ * no host round trip.  Material ids are not range-checked on this path. */
+int dsrt_scene_upload_device(dsrt_ctx* ctx,
+                             const DsrtTriangle* tris_device, int ntris,
+                             const DsrtMaterial* mats_device, int nmats, int nspheres,
+                             const DsrtTextureHeader* textures_device, int ntextures,
+                             const float* texture_pool_device, int texture_pool_floats);
+int dsrt_scene_stats(dsrt_ctx* ctx, DsrtSceneStats* out);
+/* Debug/verification: copies the wide BVH back (80-byte nodes, 48-byte triangle records). */
+int dsrt_scene_download(dsrt_ctx* ctx, void* nodes, size_t node_bytes, void* tri_records, size_t tri_bytes);
+
+/* ---- render: replaces gpu_render_scene() ---------------------------------------------
+ * Renders samples [sample_begin, sample_end) of every pixel of `rect` (x0,y0,x1,y1, half
+ * open, y = 0 is the bottom row as in the reference; NULL = whole image) and ADDS the
+ * per-sample clamped radiance into the ctx's float accumulation buffer (W*H*3, pixel-major,
+ * row 0 = bottom).  The buffer is zeroed when sample_begin == 0 or the image size changes,
+ * unless `keep_accum` is non-zero.  params->samples_per_pixel is the frame's total spp
+ * (the sample jitter divides by it); max_depth, gamma and rng_mode are honoured, the other
+ * fields are carried but unused, exactly as in the reference kernel.
+ *
+ * sun_dir is the reference's scene.sun_dir (model origin -> Sun; the estimator lights from
+ * -sun_dir, gpu_render.cu:802-806), sun_radiance its scene.sun_radiance. */
+int dsrt_render_frame(dsrt_ctx* ctx,
+                      const DsrtCamera* camera,
+                      const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                      const DsrtRenderParams* params, uint64_t seed,
+                      int sample_begin, int sample_end,
+                      const int rect[4], int keep_accum);
+int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out);
+/* 1 = time the traversal / shading kernels separately with CUDA events (adds launches of
+ * event records only; default 0). */
+int dsrt_set_stage_timing(dsrt_ctx* ctx, int enabled);
+/* Samples of a pixel that are in flight together in Philox mode (0 = choose from the image
+ * size).  The LCG replay always uses 1. */
+int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples);
+
+/* Tone-map the accumulation buffer exactly as the reference kernel's tail
+ * (gpu_render.cu:1003-1030: mean over total_spp, max 0, min 10, powf(c, 1/gamma), clamp,
+ * (uchar)(255.99f*c), row flip) and copy W*H*3 bytes, top row first, to `dst`. */
+int dsrt_readback_rgb8(dsrt_ctx* ctx, int total_spp, float gamma, unsigned char* dst, size_t bytes);
+/* Raw accumulation buffer (sum over samples of clamp01(L)), W*H*3 floats, row 0 = bottom. */
+int dsrt_readback_accum(dsrt_ctx* ctx, float* dst, size_t bytes);
+/* Device pointer / element count of the accumulation buffer, for an NCCL sum-reduce issued
+ * by the caller (single-frame sample sharding). */
+int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_floats);
+/* Replace the accumulation buffer contents from host memory (root of a host-side reduce). */
+int dsrt_upload_accum(dsrt_ctx* ctx, const float* src, size_t bytes);
+
+/* ---- parity hooks ----------------------------------------------------------------------
+ * Closest hit of n rays: rays = n x {ox,oy,oz,tmin, dx,dy,dz,tmax} floats.  Outputs per ray:
+ * tri (index into the uploaded triangle array, -1 = miss), t, u, v (barycentrics), bit-equal
+ * to hit_triangle_index()'s arithmetic (gpu_render.cu:322-353). */
+int dsrt_trace_closest(dsrt_ctx* ctx, const float* rays, int n,
+                       int32_t* tri, float* t, float* u, float* v);
+/* Any hit in [tmin,tmax] (the sun shadow-ray query, gpu_render.cu:812-816): occluded[i]=0/1. */
+int dsrt_trace_occluded(dsrt_ctx* ctx, const float* rays, int n, uint8_t* occluded);
+/* Primary rays of the reference camera with a fixed sub-pixel jitter (jx,jy) for every
+ * pixel (gpu_render.cu:941-968), traced for the first hit.  Outputs are W*H, index
+ * x + y*W with y = 0 the bottom row. */
+int dsrt_first_hits(dsrt_ctx* ctx, const DsrtCamera* camera, int width, int height,
+                    float jx, float jy, int32_t* tri, float* t, float* u, float* v);
+/* Device-resident closest-hit / any-hit over rays already in device memory (bench of the
+ * traversal kernel alone).  rays_device: n x 8 floats; hits_device: n x 4 floats
+ * {t,u,v,bits(tri)}; occluded_device: n bytes. */
+int dsrt_trace_closest_device(dsrt_ctx* ctx, const void* rays_device, int n, void* hits_device);
+int dsrt_trace_occluded_device(dsrt_ctx* ctx, const void* rays_device, int n, void* occluded_device);
+
+/* ---- host side of the path (no GPU needed) ---------------------------------------------
+ * Pose file: reference read_pose_file(), /root/reference/src/main.cpp:139-173.  Returns the
+ * number of poses found (>= 0) or DSRT_EIO; writes at most max_poses x 9 doubles
+ * {cam xyz, model xyz, yaw, pitch, roll}.  yaw/pitch/roll pass through float as in the
+ * reference (PoseEntry::model_euler_deg is a float vec3). */
+int dsrt_read_pose_file(const char* path, double* poses9, int max_poses);
+/* World -> model frame in double, then cast: main.cpp:334-357 with rotate_yaw_deg_d
+ * (main.cpp:118-128).  sep_m is |cam - model|; frames with sep_m < 1 are skipped by the
+ * reference (main.cpp:340-345). */
+void dsrt_pose_to_model_frame(const double pose9[9], float cam_in_model[3],
+                              float sun_dir_model[3], double* sep_m);
+/* point_camera_at() + camera::initialize(): main.cpp:178-187, inc/camera.h:91-116
+ * (vup = +y, lookat = origin, focus = |lookfrom|, aperture 0, float math). */
+void dsrt_camera_look_at_origin(const float lookfrom[3], float vfov_deg, int width, int height,
+                                int spp, int max_depth, DsrtCamera* out);
+/* Deterministic synthetic "station" mesh standing in for the ISS OBJ.
+ * Writes ntris triangles and up to max_mats materials; returns the number of materials.
+ * diffuse_only != 0 gives lambertian-only materials (BASELINE config 5). */
+int dsrt_synth_mesh(int ntris, uint32_t seed, int diffuse_only,
+                    DsrtTriangle* tris, DsrtMaterial* mats, int max_mats);
+/* Binary P6 exactly as gpu_render.cu:1100-1107 writes it; PNG (8-bit RGB, zlib) replaces
+ * the ImageMagick subprocess of main.cpp:28-36. */
+int dsrt_write_ppm(const char* path, const unsigned char* rgb, int width, int height);
+int dsrt_write_png(const char* path, const unsigned char* rgb, int width, int height);
+
+/* Library build identification ("dsrt-b200 <n> sm_100a"). */
+const char* dsrt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DSRT_H */
