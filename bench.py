@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the render hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode frame|sample]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one frame of BASELINE.json's config 2: pose 0 of the
+shipped pose file, the synthetic 1M-triangle station, 1920x1080, 64 spp, depth 10, directional
+sun with shadow rays.  Metric: Mrays/s (primary + bounce + shadow rays traced / device time).
+
+  value      scene resident in HBM, CUDA events on the ctx stream around each step, L2
+             flushed between steps, max over ranks
+  e2e        the same frames through the C ABI with host buffers: camera/sun/params passed
+             from host memory, tone-mapped RGB8 frame read back to host every step
+  roofline   closest-hit traversal kernel (k_extend): algorithmic bytes B(N) x rays / its
+             summed launch durations (CUDA events), against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's CPU camera/bvh_node path (oracle/_ref/libref_cpu.so) on the
+             host cores, on a bounded sample of the same frame (rank 0, N = 1 only)
+
+N > 1: frame-parallel -- rank r renders pose (step*N + r) of the sequence, no collective
+(scaling "weak": per-GPU work fixed).  --mode sample shards ONE frame's samples over the
+ranks and sums the float accumulation buffers with one NCCL reduce ("strong").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+POSE_FILE = ROOT / "tests" / "golden" / "rendezvous_1s_dt0_01s.txt"
+
+
+def algorithmic_bytes_per_ray(ntris: int) -> float:
+    """ray in (32 B) + hit out (16 B) + one root-to-leaf path through an 8-wide
+    BVH of 80-byte nodes + a 4-triangle leaf of 48-byte records."""
+    levels = max(1, math.ceil(math.log(max(ntris, 8) / 4.0, 8)))
+    return 48.0 + 80.0 * levels + 4 * 48.0
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dsrt", choices=["dsrt", "reference"])
+    ap.add_argument("--mode", default="frame", choices=["frame", "sample"])
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--depth", type=int, default=10)
+    ap.add_argument("--diffuse_only", action="store_true")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--cpu_step", type=int, default=8, help="pixel stride of the CPU sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"pose 0 of rendezvous_1s_dt0_01s.txt, synthetic {a.tris}-triangle station"
+            f"{' (diffuse only)' if a.diffuse_only else ''}, {a.width}x{a.height}, {a.spp} spp, depth {a.depth}, "
+            "directional sun + shadow rays")
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
+    """The reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    import dsrt_b200 as d          # host helpers only (mesh, pose); no GPU call is made here
+    import refcpu
+    poses = d.read_pose_file(POSE_FILE)
+    cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+    tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
+    step = max(1, a.cpu_step)
+    sample = (f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, 1 of {a.spp} samples per step "
+              f"(sample index = step), all {a.depth} bounces")
+    if refcpu.available():
+        kind = "reference"
+        sc = refcpu.RefCpuScene(tris, mats)
+        cores = os.cpu_count() or 1
+        build_s = sc.build_s
+
+        def one(i):
+            s, c = sc.render(cam_pos, sun, a.width, a.height, a.spp, a.depth, step_x=step, step_y=step,
+                             s_begin=i % a.spp, s_end=i % a.spp + 1, threads=cores)
+            return s, int(c.sum())
+    else:
+        import oracle
+        kind = "port"
+        t0 = time.perf_counter()
+        sc = oracle.Scene(tris, mats)
+        build_s = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        cam = d.camera_look_at_origin(cam_pos, 40.0, a.width // step, a.height // step)
+        cam12 = np.array(cam.origin.tuple() + cam.lower_left_corner.tuple() + cam.horizontal.tuple() + cam.vertical.tuple(), np.float32)
+
+        def one(i):
+            t0 = time.perf_counter()
+            _, _, c = sc.render(cam12, a.width // step, a.height // step, a.spp, a.depth, sun, rng_mode=1,
+                                s_begin=i % a.spp, s_end=i % a.spp + 1)
+            return time.perf_counter() - t0, int(c.sum())
+    for i in range(a.warmup):
+        one(i)
+    secs = rays = 0
+    for i in range(a.steps):
+        s, r = one(a.warmup + i)
+        secs += s
+        rays += r
+    v = rays / secs / 1e6
+    out = {
+        "impl": "reference", "metric": "Mrays/s (primary+bounce+shadow)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample, "bvh_build_s": build_s},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_dsrt(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import dsrt_b200 as d
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    poses = d.read_pose_file(POSE_FILE)
+    tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
+    ctx = d.Context(local_rank)
+    st = ctx.upload_scene(tris, mats)
+    ctx.set_stage_timing(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    params = d.make_params(a.width, a.height, a.spp, a.depth, d.RNG_PHILOX)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    rgb = np.empty((a.height, a.width, 3), np.uint8)
+
+    def frame_inputs(i):
+        idx = (i * world + rank) % len(poses) if (world > 1 and a.mode == "frame") else 0
+        cam_pos, sun, _ = d.pose_to_model_frame(poses[idx])
+        return d.camera_look_at_origin(cam_pos, 40.0, a.width, a.height, a.spp, a.depth), sun
+
+    s_lo, s_hi = 0, a.spp
+    if world > 1 and a.mode == "sample":
+        s_lo, s_hi = a.spp * rank // world, a.spp * (rank + 1) // world
+        acc_ptr = None
+
+    def reduce_accum():
+        # one NCCL sum-reduce of the float accumulation buffer to rank 0 (NVLink/NVSwitch)
+        ptr, n = ctx.accum_device()
+
+        class _P:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        t = torch.as_tensor(_P(), device=dev)
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+
+    def step(i, timed):
+        cam, sun = frame_inputs(i)
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fs = ctx.render(cam, sun, params, sample_begin=s_lo, sample_end=s_hi)
+        if world > 1 and a.mode == "sample":
+            with torch.cuda.stream(stream):
+                reduce_accum()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), fs
+
+    for i in range(a.warmup):
+        step(i, False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms = rays = launches = ext_ms = ext_rays = 0.0
+    for i in range(a.steps):
+        m, fs = step(a.warmup + i, True)
+        ms += m
+        rays += fs.rays
+        launches += fs.kernel_launches
+        ext_ms += fs.extend_ms
+        ext_rays += fs.primary_rays + fs.bounce_rays
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+
+    # ---- end to end through the C ABI with host buffers (render + tone-map + D2H each step)
+    e2e_ms = e2e_rays = 0.0
+    if not a.no_e2e:
+        for i in range(a.steps):
+            cam, sun = frame_inputs(a.warmup + i)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fs = ctx.render(cam, sun, params, sample_begin=s_lo, sample_end=s_hi)
+            if world > 1 and a.mode == "sample":
+                with torch.cuda.stream(stream):
+                    reduce_accum()
+                torch.cuda.synchronize(dev)
+            if not (world > 1 and a.mode == "sample" and rank != 0):
+                ctx.readback_rgb8(a.spp, params.gamma, rgb)
+            e2e_ms += 1e3 * (time.perf_counter() - t0)
+            e2e_rays += fs.rays
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+        s = torch.tensor([rays, e2e_rays, launches, ext_ms, ext_rays], dtype=torch.float64, device=dev)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        rays, e2e_rays, launches, ext_ms, ext_rays = s.tolist()
+        ext_ms /= world            # average per-rank time of the traversal kernel
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        bpr = algorithmic_bytes_per_ray(a.tris)
+        achieved = (ext_rays / world) * bpr / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        traffic = None
+        prof = ROOT / "profiles" / "extend_ncu_summary.json"
+        if prof.exists():
+            try:
+                traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        out = {
+            "metric": "Mrays/s (primary+bounce+shadow)", "value": rays / (ms * 1e3), "unit": "Mrays/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "strong" if (world > 1 and a.mode == "sample") else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": f"{a.mode}-parallel x{world}" if world > 1 else "single GPU",
+                       "rng": "philox4x32-10", "l2": "flushed between steps (256 MiB write)",
+                       "frames_per_s": world * a.steps / (ms * 1e-3) if a.mode == "frame" else a.steps / (ms * 1e-3),
+                       "bvh": {"wide_nodes": st.num_wide_nodes, "levels": st.num_levels, "build_ms": st.build_ms,
+                               "upload_ms": st.upload_ms, "sah": st.sah_cost}},
+            "clocks": clk,
+            "e2e": {"value": (e2e_rays / (e2e_ms * 1e3)) if e2e_ms else None, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": 104 + 48 + 24 + 8, "d2h_bytes_per_step": a.width * a.height * 3,
+                    "ms_per_step": e2e_ms / a.steps if e2e_ms else None},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH8 traversal)", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                         "bytes_per_ray": bpr, "rays_per_step": ext_rays / world / a.steps,
+                         "kernel_ms_per_step": ext_ms / a.steps, "traffic": traffic},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(a, tris, mats, poses)
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, tris, mats, poses):
+    """The reference CPU path on a bounded sample of the same frame (rank 0, N = 1)."""
+    import dsrt_b200 as d
+    cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+    step = max(1, a.cpu_step)
+    cores = os.cpu_count() or 1
+    sample = f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, 2 of {a.spp} samples, depth {a.depth}"
+    try:
+        import refcpu
+        if refcpu.available():
+            sc = refcpu.RefCpuScene(tris, mats)
+            secs, c = sc.render(cam_pos, sun, a.width, a.height, a.spp, a.depth, step_x=step, step_y=step, s_begin=0, s_end=2, threads=cores)
+            return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                    "sample": sample, "bvh_build_s": sc.build_s, "seconds": secs}
+        import oracle
+        sc = oracle.Scene(tris, mats)
+        w, h = a.width // step, a.height // step
+        cam = d.camera_look_at_origin(cam_pos, 40.0, w, h)
+        cam12 = np.array(cam.origin.tuple() + cam.lower_left_corner.tuple() + cam.horizontal.tuple() + cam.vertical.tuple(), np.float32)
+        t0 = time.perf_counter()
+        _, _, c = sc.render(cam12, w, h, a.spp, a.depth, sun, rng_mode=1, s_begin=0, s_end=2)
+        secs = time.perf_counter() - t0
+        return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                "sample": f"{w}x{h} down-sampled frame, 2 of {a.spp} samples, depth {a.depth}", "seconds": secs}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_dsrt(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,43 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* ---- minimal parallel-for over rows / ray chunks (pthreads; OpenMP is not in this image) ---- */
+typedef void (*or_job_fn)(int index, void* arg);
+typedef struct { or_job_fn fn; void* arg; int n; int next; pthread_mutex_t mu; } OrPool;
+
+static void* or_worker(void* p) {
+    OrPool* pool = (OrPool*)p;
+    for (;;) {
+        pthread_mutex_lock(&pool->mu);
+        int i = pool->next++;
+        pthread_mutex_unlock(&pool->mu);
+        if (i >= pool->n) break;
+        pool->fn(i, pool->arg);
+    }
+    return NULL;
+}
+
+static int or_threads = 0;
+void or_set_threads(int n) { or_threads = n; }
+int or_get_threads(void) {
+    if (or_threads > 0) return or_threads;
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+static void or_parallel_for(int n, or_job_fn fn, void* arg) {
+    int nt = or_get_threads();
+    if (nt > n) nt = n;
+    if (nt <= 1) { for (int i = 0; i < n; ++i) fn(i, arg); return; }
+    OrPool pool = {fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER};
+    pthread_t th[256];
+    if (nt > 256) nt = 256;
+    for (int t = 0; t < nt; ++t) pthread_create(&th[t], NULL, or_worker, &pool);
+    for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+}
 
 typedef struct { float x, y, z; } f3;
 
@@ -444,48 +481,63 @@ static Ray camera_ray(const float c[12], int px, int py, int W, int H, float jx,
     return r;
 }
 
+typedef struct {
+    const OrScene* s; const float* cam12; int W, H; float jx, jy;
+    int32_t* tri; float *t, *u, *v;
+} FirstHitJob;
+
+static void first_hit_row(int y, void* arg) {
+    FirstHitJob* J = (FirstHitJob*)arg;
+    for (int x = 0; x < J->W; ++x) {
+        Ray r = camera_ray(J->cam12, x, y, J->W, J->H, J->jx, J->jy);
+        Hit rec;
+        int hit = scene_hit(J->s, &r, 0.001f, 1e9f, &rec);
+        int i = x + y * J->W;
+        J->tri[i] = hit ? rec.tri_index : -1;
+        J->t[i] = hit ? rec.t : 1e9f;
+        J->u[i] = hit ? rec.u : 0.f;
+        J->v[i] = hit ? rec.v : 0.f;
+    }
+}
+
 void or_first_hits(const OrScene* s, const float cam12[12], int W, int H, float jx, float jy,
                    int32_t* tri, float* t, float* u, float* v) {
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-            Ray r = camera_ray(cam12, x, y, W, H, jx, jy);
-            Hit rec;
-            int hit = scene_hit(s, &r, 0.001f, 1e9f, &rec);
-            int i = x + y * W;
-            tri[i] = hit ? rec.tri_index : -1;
-            t[i] = hit ? rec.t : 1e9f;
-            u[i] = hit ? rec.u : 0.f;
-            v[i] = hit ? rec.v : 0.f;
-        }
+    FirstHitJob J = {s, cam12, W, H, jx, jy, tri, t, u, v};
+    or_parallel_for(H, first_hit_row, &J);
+}
+
+#define OR_CHUNK 1024
+typedef struct {
+    const OrScene* s; const float* rays; int n;
+    int32_t* tri; float *t, *u, *v; uint8_t* occ;
+} TraceJob;
+
+static void trace_chunk(int c, void* arg) {
+    TraceJob* J = (TraceJob*)arg;
+    int end = (c + 1) * OR_CHUNK < J->n ? (c + 1) * OR_CHUNK : J->n;
+    for (int i = c * OR_CHUNK; i < end; ++i) {
+        const float* q = J->rays + (size_t)i * 8;
+        Ray r;
+        r.orig = F3(q[0], q[1], q[2]);
+        r.dir = F3(q[4], q[5], q[6]);
+        Hit rec;
+        int hit = scene_hit(J->s, &r, q[3], q[7], &rec);
+        if (J->occ) { J->occ[i] = (uint8_t)hit; continue; }
+        J->tri[i] = hit ? rec.tri_index : -1;
+        J->t[i] = hit ? rec.t : q[7];
+        J->u[i] = hit ? rec.u : 0.f;
+        J->v[i] = hit ? rec.v : 0.f;
+    }
 }
 
 void or_trace(const OrScene* s, const float* rays, int n, int32_t* tri, float* t, float* u, float* v) {
-#pragma omp parallel for schedule(dynamic, 256)
-    for (int i = 0; i < n; ++i) {
-        const float* q = rays + (size_t)i * 8;
-        Ray r;
-        r.orig = F3(q[0], q[1], q[2]);
-        r.dir = F3(q[4], q[5], q[6]);
-        Hit rec;
-        int hit = scene_hit(s, &r, q[3], q[7], &rec);
-        tri[i] = hit ? rec.tri_index : -1;
-        t[i] = hit ? rec.t : q[7];
-        u[i] = hit ? rec.u : 0.f;
-        v[i] = hit ? rec.v : 0.f;
-    }
+    TraceJob J = {s, rays, n, tri, t, u, v, NULL};
+    or_parallel_for((n + OR_CHUNK - 1) / OR_CHUNK, trace_chunk, &J);
 }
 
 void or_occluded(const OrScene* s, const float* rays, int n, uint8_t* occluded) {
-#pragma omp parallel for schedule(dynamic, 256)
-    for (int i = 0; i < n; ++i) {
-        const float* q = rays + (size_t)i * 8;
-        Ray r;
-        r.orig = F3(q[0], q[1], q[2]);
-        r.dir = F3(q[4], q[5], q[6]);
-        Hit rec;
-        occluded[i] = (uint8_t)scene_hit(s, &r, q[3], q[7], &rec);
-    }
+    TraceJob J = {s, rays, n, NULL, NULL, NULL, NULL, occluded};
+    or_parallel_for((n + OR_CHUNK - 1) / OR_CHUNK, trace_chunk, &J);
 }
 
 /* gpu_render.cu:1003-1030 */
@@ -505,39 +557,59 @@ void or_tonemap(const float* accum, int W, int H, int spp_total, float gamma, un
 }
 
 /* render_kernel, gpu_render.cu:973-1031 */
+typedef struct {
+    const OrScene* s; const float* cam12; int W, H, spp, max_depth, sun_enabled, rng_mode, s_begin, s_end;
+    f3 sd, sr; uint64_t seed; float* accum; uint32_t* lcg_state;
+    uint64_t counts[3]; pthread_mutex_t mu;
+} RenderJob;
+
+static void render_row(int y, void* arg) {
+    RenderJob* J = (RenderJob*)arg;
+    Counts cnt = {0, 0, 0};
+    for (int x = 0; x < J->W; ++x) {
+        Rng rng;
+        memset(&rng, 0, sizeof(rng));
+        rng.mode = J->rng_mode;
+        rng.pixel = (uint32_t)(x + y * J->W);
+        rng.k0 = (uint32_t)(J->seed & 0xFFFFFFFFu);
+        rng.k1 = (uint32_t)(J->seed >> 32);
+        if (J->rng_mode == 1)
+            rng.state = (J->lcg_state && J->s_begin > 0) ? J->lcg_state[rng.pixel]
+                                                         : (rng.pixel ^ (uint32_t)(J->seed & 0xFFFFFFFFu));   /* :990 */
+        float* a = J->accum + ((size_t)y * J->W + x) * 3;
+        for (int sidx = J->s_begin; sidx < J->s_end; ++sidx) {
+            if (J->rng_mode != 1) { rng.state = 0u; rng.sample = (uint32_t)sidx; }
+            const float jx = ((float)sidx + rand01(&rng)) / (float)J->spp;      /* :995-996 */
+            const float jy = ((float)sidx + rand01(&rng)) / (float)J->spp;
+            Ray ray = camera_ray(J->cam12, x, y, J->W, J->H, jx, jy);
+            f3 c = ray_color(J->s, ray, &rng, J->max_depth, J->sun_enabled, J->sd, J->sr, &cnt);
+            a[0] += c.x; a[1] += c.y; a[2] += c.z;
+        }
+        if (J->rng_mode == 1 && J->lcg_state) J->lcg_state[rng.pixel] = rng.state;
+    }
+    pthread_mutex_lock(&J->mu);
+    J->counts[0] += cnt.primary; J->counts[1] += cnt.bounce; J->counts[2] += cnt.shadow;
+    pthread_mutex_unlock(&J->mu);
+}
+
 void or_render(const OrScene* s, const float cam12[12], int W, int H, int spp_total, int max_depth,
                const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
                uint64_t seed, int rng_mode, float gamma, int s_begin, int s_end,
                float* accum, unsigned char* rgb, uint32_t* lcg_state, uint64_t ray_counts[3]) {
-    const int spp = spp_total < 1 ? 1 : spp_total;
-    const f3 sd = F3(sun_dir[0], sun_dir[1], sun_dir[2]), sr = F3(sun_radiance[0], sun_radiance[1], sun_radiance[2]);
-    uint64_t c_primary = 0, c_bounce = 0, c_shadow = 0;
-#pragma omp parallel for schedule(dynamic, 2) reduction(+ : c_primary, c_bounce, c_shadow)
-    for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-            Rng rng;
-            rng.mode = rng_mode;
-            rng.pixel = (uint32_t)(x + y * W);
-            rng.k0 = (uint32_t)(seed & 0xFFFFFFFFu);
-            rng.k1 = (uint32_t)(seed >> 32);
-            if (rng_mode == 1)
-                rng.state = (lcg_state && s_begin > 0) ? lcg_state[rng.pixel]
-                                                       : (rng.pixel ^ (uint32_t)(seed & 0xFFFFFFFFu));
-            float* a = accum + ((size_t)y * W + x) * 3;
-            Counts cnt = {0, 0, 0};
-            for (int sidx = s_begin; sidx < s_end; ++sidx) {
-                if (rng_mode != 1) { rng.state = 0u; rng.sample = (uint32_t)sidx; }
-                const float jx = ((float)sidx + rand01(&rng)) / (float)spp;
-                const float jy = ((float)sidx + rand01(&rng)) / (float)spp;
-                Ray ray = camera_ray(cam12, x, y, W, H, jx, jy);
-                f3 c = ray_color(s, ray, &rng, max_depth, sun_enabled, sd, sr, &cnt);
-                a[0] += c.x; a[1] += c.y; a[2] += c.z;
-            }
-            if (rng_mode == 1 && lcg_state) lcg_state[rng.pixel] = rng.state;
-            c_primary += cnt.primary; c_bounce += cnt.bounce; c_shadow += cnt.shadow;
-        }
-    if (ray_counts) { ray_counts[0] += c_primary; ray_counts[1] += c_bounce; ray_counts[2] += c_shadow; }
-    if (rgb) or_tonemap(accum, W, H, spp, gamma, rgb);
+    RenderJob J;
+    memset(&J, 0, sizeof(J));
+    J.s = s; J.cam12 = cam12; J.W = W; J.H = H;
+    J.spp = spp_total < 1 ? 1 : spp_total;
+    J.max_depth = max_depth; J.sun_enabled = sun_enabled; J.rng_mode = rng_mode;
+    J.s_begin = s_begin; J.s_end = s_end;
+    J.sd = F3(sun_dir[0], sun_dir[1], sun_dir[2]);
+    J.sr = F3(sun_radiance[0], sun_radiance[1], sun_radiance[2]);
+    J.seed = seed; J.accum = accum; J.lcg_state = lcg_state;
+    pthread_mutex_init(&J.mu, NULL);
+    or_parallel_for(H, render_row, &J);
+    pthread_mutex_destroy(&J.mu);
+    if (ray_counts) { ray_counts[0] += J.counts[0]; ray_counts[1] += J.counts[1]; ray_counts[2] += J.counts[2]; }
+    if (rgb) or_tonemap(accum, W, H, J.spp, gamma, rgb);
 }
 
 /* ---- host side ----------------------------------------------------------------------------- */

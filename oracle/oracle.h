@@ -56,6 +56,10 @@ int  or_read_pose_file(const char* path, double* poses9, int max_poses);
 void or_pose_to_model_frame(const double pose9[9], float cam_in_model[3], float sun_dir_model[3], double* sep_m);
 void or_camera_init(const float lookfrom[3], float vfov_deg, int W, int H, float cam12[12], float uvw9[9]);
 
+/* Worker threads of the parallel loops (default: all online cores). */
+void or_set_threads(int n);
+int  or_get_threads(void);
+
 /* Philox4x32-10 known-answer hook: writes the 4 outputs for (ctr, key). */
 void or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
