@@ -121,6 +121,7 @@ def parse_args():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--cpu_step", type=int, default=8, help="pixel stride of the CPU sample")
+    ap.add_argument("--spb", type=int, default=0, help="samples of a pixel in flight together (0 = library default)")
     return ap.parse_args()
 
 
@@ -206,6 +207,8 @@ def run_dsrt(a, rank, world, local_rank):
     ctx = d.Context(local_rank)
     st = ctx.upload_scene(tris, mats)
     ctx.set_stage_timing(True)
+    if a.spb > 0:
+        ctx.set_samples_per_batch(a.spb)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     params = d.make_params(a.width, a.height, a.spp, a.depth, d.RNG_PHILOX)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
