@@ -12,8 +12,9 @@ sun with shadow rays.  Metric: Mrays/s (primary + bounce + shadow rays traced / 
              flushed between steps, max over ranks
   e2e        the same frames through the C ABI with host buffers: camera/sun/params passed
              from host memory, tone-mapped RGB8 frame read back to host every step
-  roofline   closest-hit traversal kernel (k_extend): algorithmic bytes B(N) x rays / its
-             summed launch durations (CUDA events), against MEASURED_PEAKS.json hbm_gbs
+  roofline   BVH traversal kernels (k_primary + k_trace share one traversal loop): algorithmic
+             bytes B(N) x rays / their summed launch durations (CUDA events on the ctx stream),
+             against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference's CPU camera/bvh_node path (oracle/_ref/libref_cpu.so) on the
              host cores, on a bounded sample of the same frame (rank 0, N = 1 only)
 
@@ -261,7 +262,7 @@ def run_dsrt(a, rank, world, local_rank):
         rays += fs.rays
         launches += fs.kernel_launches
         ext_ms += fs.extend_ms
-        ext_rays += fs.primary_rays + fs.bounce_rays
+        ext_rays += fs.rays
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -319,7 +320,7 @@ def run_dsrt(a, rank, world, local_rank):
                     "h2d_bytes_per_step": 104 + 48 + 24 + 8, "d2h_bytes_per_step": a.width * a.height * 3,
                     "ms_per_step": e2e_ms / a.steps if e2e_ms else None},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH8 traversal)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "k_primary + k_trace (BVH8 traversal, closest and any hit)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_ray": bpr, "rays_per_step": ext_rays / world / a.steps,
                          "kernel_ms_per_step": ext_ms / a.steps, "traffic": traffic},

@@ -17,7 +17,8 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libdsrt.so"
+# DSRT_LIB selects another build of the same library (kernel-variant experiments only).
+LIB_PATH = Path(os.environ["DSRT_LIB"]) if os.environ.get("DSRT_LIB") else _HERE / "libdsrt.so"
 
 if not LIB_PATH.exists():
     raise ImportError(

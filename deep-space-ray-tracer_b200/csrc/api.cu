@@ -429,14 +429,16 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
         for (int a = 0; a < 3; ++a) fc.sun_rad[a] = sun_radiance[a];
     }
 
-    // samples of a pixel in flight together
+    // Samples of a pixel in flight together.  Large batches keep the deep-bounce launches
+    // (few surviving rays) big enough to fill the GPU (profiles/r01_a: 2x from spb 4 -> 32);
+    // the default takes as many samples as fit a ~20 GB work-memory budget (144 B per path).
     int spb = 1;
     const int nsamples = sample_end - sample_begin;
     if (rng_mode == DSRT_RNG_PHILOX) {
         if (ctx->spb_override > 0) spb = ctx->spb_override;
         else {
-            const long long target = 8ll << 20;   // ~8M paths per batch
-            spb = (int)std::max(1ll, std::min(64ll, target / std::max(1, fc.slots_per_sample)));
+            const long long target = 20ll * 1000 * 1000 * 1000 / 144;
+            spb = (int)std::max(1ll, std::min(256ll, target / std::max(1, fc.slots_per_sample)));
         }
         spb = std::max(1, std::min(spb, std::max(1, nsamples)));
     }
@@ -453,44 +455,48 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     CK(cudaEventRecord(ctx->ev_frame[0], ctx->stream));
 
     uint32_t launches = 0, batches = 0;
-    size_t nev = 0;                 // events used from the pool (pairs: extend, shadow)
-    std::vector<int> ev_kind;       // 0 = extend, 1 = shadow
+    size_t nev = 0;                 // events used from the pool
+    std::vector<int> ev_kind;       // what the interval [k, k+1) measured: 0 traversal, 1 shade, -1 other
     const bool timing = ctx->stage_timing != 0;
+    auto mark = [&](int kind_of_next_interval) {
+        if (!timing || nev >= (size_t)kMaxEvents) return;
+        cudaEvent_t e = pool_event(ctx, nev);
+        if (!e) return;
+        cudaEventRecord(e, ctx->stream);
+        ev_kind.push_back(kind_of_next_interval);
+        ++nev;
+    };
 
     for (int s0 = sample_begin; s0 < sample_end; s0 += spb) {
         fc.s0 = s0;
         fc.spb = std::min(spb, sample_end - s0);
         launch_batch_begin(fc, ctx->stream);
-        launch_raygen(fc, ctx->dims, ctx->stream);
+        mark(0);
+        launch_primary(fc, ctx->dims, ctx->stream);
         launches += 2;
         int cur = 0;
         for (int depth = 0; depth < fc.max_depth; ++depth) {
-            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
-            if (timing && nev + 4 <= (size_t)kMaxEvents) {
-                e0 = pool_event(ctx, nev); e1 = pool_event(ctx, nev + 1);
-                e2 = pool_event(ctx, nev + 2); e3 = pool_event(ctx, nev + 3);
-            }
-            if (e0) cudaEventRecord(e0, ctx->stream);
-            launch_extend(fc, cur, ctx->dims, ctx->stream);
-            if (e1) cudaEventRecord(e1, ctx->stream);
+            mark(1);
             launch_shade(fc, cur, depth, ctx->dims, ctx->stream);
-            if (e2) cudaEventRecord(e2, ctx->stream);
-            launch_shadow(fc, ctx->dims, ctx->stream);
-            if (e3) { cudaEventRecord(e3, ctx->stream); nev += 4; }
+            mark(-1);
             launch_advance(fc, depth, ctx->stream);
-            launches += 4;
+            mark(0);
+            launch_trace(fc, cur ^ 1, depth & 1, ctx->dims, ctx->stream);
+            launches += 3;
             cur ^= 1;
-            // Long depth limits (the reference default is 50): stop once the queue is empty.
+            // Long depth limits (the reference default is 50): stop once nothing is in flight.
             if (depth >= 7 && (depth & 3) == 3 && depth + 1 < fc.max_depth) {
-                CK(cudaMemcpyAsync(ctx->h_pinned, ctx->counters + C_NIN, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->h_pinned, ctx->counters, sizeof(uint32_t) * C_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
-                if (ctx->h_pinned[0] == 0u) break;
+                if (ctx->h_pinned[C_NIN] == 0u) break;      // shadow rays of this bounce were traced above
             }
         }
+        mark(-1);
         launch_resolve(fc, ctx->dims, ctx->stream);
         ++launches;
         ++batches;
     }
+    mark(-1);
     CK(cudaEventRecord(ctx->ev_frame[1], ctx->stream));
     CK(cudaGetLastError());
     unsigned long long hs[S_COUNT];
@@ -506,15 +512,14 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     fs.batches = batches;
     cudaEventElapsedTime(&fs.device_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
     if (timing) {
-        float ext = 0.f, shd = 0.f, shade = 0.f;
-        for (size_t k = 0; k + 3 < nev; k += 4) {
-            float a = 0.f, b = 0.f, c = 0.f;
-            cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-            cudaEventElapsedTime(&b, ctx->ev_pool[k + 1], ctx->ev_pool[k + 2]);
-            cudaEventElapsedTime(&c, ctx->ev_pool[k + 2], ctx->ev_pool[k + 3]);
-            ext += a; shade += b; shd += c;
+        float trav = 0.f, shade = 0.f;
+        for (size_t k = 0; k + 1 < nev; ++k) {
+            float ms = 0.f;
+            if (ev_kind[k] < 0) continue;
+            cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+            if (ev_kind[k] == 0) trav += ms; else shade += ms;
         }
-        fs.extend_ms = ext; fs.shadow_ms = shd; fs.shade_ms = shade;
+        fs.extend_ms = trav; fs.shadow_ms = 0.f; fs.shade_ms = shade;
     }
     ctx->fstats = fs;
     return DSRT_OK;
@@ -598,7 +603,7 @@ extern "C" int dsrt_trace_closest_device(dsrt_ctx* ctx, const void* rays_device,
     CK(cudaSetDevice(ctx->device));
     launch_trace_closest(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
                          (const float4*)rays_device, n, (float4*)hits_device,
-                         ctx->counters + C_FETCH_EXT, ctx->dims.extend_blocks, ctx->stream);
+                         ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());
     return DSRT_OK;
 }
@@ -610,7 +615,7 @@ extern "C" int dsrt_trace_occluded_device(dsrt_ctx* ctx, const void* rays_device
     CK(cudaSetDevice(ctx->device));
     launch_trace_occluded(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
                           (const float4*)rays_device, n, (uint8_t*)occluded_device,
-                          ctx->counters + C_FETCH_SHD, ctx->dims.shadow_blocks, ctx->stream);
+                          ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());
     return DSRT_OK;
 }

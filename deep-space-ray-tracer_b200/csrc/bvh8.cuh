@@ -107,6 +107,22 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     return ((x >> 7) & 0x01010101u) * 0xFFu;
 }
 
+// Byte j of a packed word as a float.  I2F.U8 runs on the XU pipe (16 lanes/clk/SM) and 48 of
+// them per node visit saturate it (profiles/r01_a: XU 81 % busy).  The alternative builds the
+// float 2^23 + byte with one PRMT (ALU pipe) and subtracts 2^23 with one FADD (FMA pipe):
+// exact, and spread over the two wide pipes.  kI2fMask picks, per plane set (near x,y,z, far
+// x,y,z = bits 0..5), which conversion is used so the three pipes can be balanced.
+template <bool USE_I2F>
+__device__ __forceinline__ float byte_to_float(uint32_t w, int j) {
+    if (USE_I2F) return (float)((w >> (8 * j)) & 0xFFu);
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)) - 8388608.0f;
+}
+
+#ifndef DSRT_I2F_MASK
+#define DSRT_I2F_MASK 0x09      // near-x and far-x through I2F, the other four through PRMT+FADD
+#endif
+constexpr int kI2fMask = DSRT_I2F_MASK;
+
 // Intersects the eight child boxes of one node; returns the hit mask (bits 24..31 inner
 // children in traversal-priority order, bits 0..23 triangles).
 __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, uint32_t node_index,
@@ -133,6 +149,11 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
     const float bx = (px - ox) * idx;
     const float by = (py - oy) * idy;
     const float bz = (pz - oz) * idz;
+    // far planes widened by 2^-20 (relative): the slab test must never reject what the exact
+    // triangle test accepts, whatever the distance between ray origin and node.
+    constexpr float kWiden = 1.0f + 9.5367431640625e-07f;
+    const float ax1 = ax * kWiden, ay1 = ay * kWiden, az1 = az * kWiden;
+    const float bx1 = bx * kWiden, by1 = by * kWiden, bz1 = bz * kWiden;
 
     uint32_t hitmask = 0;
 #pragma unroll
@@ -152,12 +173,12 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int sh = 8 * j;
-            const float t0x = fmaf((float)((nx >> sh) & 0xFFu), ax, bx);
-            const float t0y = fmaf((float)((ny >> sh) & 0xFFu), ay, by);
-            const float t0z = fmaf((float)((nz >> sh) & 0xFFu), az, bz);
-            const float t1x = fmaf((float)((fx >> sh) & 0xFFu), ax, bx);
-            const float t1y = fmaf((float)((fy >> sh) & 0xFFu), ay, by);
-            const float t1z = fmaf((float)((fz >> sh) & 0xFFu), az, bz);
+            const float t0x = fmaf(byte_to_float<(kI2fMask & 1) != 0>(nx, j), ax, bx);
+            const float t0y = fmaf(byte_to_float<(kI2fMask & 2) != 0>(ny, j), ay, by);
+            const float t0z = fmaf(byte_to_float<(kI2fMask & 4) != 0>(nz, j), az, bz);
+            const float t1x = fmaf(byte_to_float<(kI2fMask & 8) != 0>(fx, j), ax1, bx1);
+            const float t1y = fmaf(byte_to_float<(kI2fMask & 16) != 0>(fy, j), ay1, by1);
+            const float t1z = fmaf(byte_to_float<(kI2fMask & 32) != 0>(fz, j), az1, bz1);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
             if (cmin <= cmax) {
@@ -170,29 +191,35 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
     return hitmask;
 }
 
-// Closest hit (ANY_HIT = false) or first hit found (ANY_HIT = true, returns as soon as one
-// triangle is accepted -- the sun shadow query only needs the boolean).
-template <bool ANY_HIT>
-__device__ __forceinline__ void traverse(const uint4* __restrict__ nodes,
-                                         const float4* __restrict__ tris,
-                                         const TravRay& ray, TravStack& stack, TravHit& hit) {
-    const V3 orig = v3(ray.ox, ray.oy, ray.oz);
-    const V3 dir = v3(ray.dx, ray.dy, ray.dz);
-    const float idx = safe_rcp_dir(ray.dx), idy = safe_rcp_dir(ray.dy), idz = safe_rcp_dir(ray.dz);
-    const uint32_t oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
-    const uint32_t octinv = 7u - oct;
-    const uint32_t octinv4 = octinv * 0x01010101u;
-    const float tmin = ray.tmin;
-    float tmax = ray.tmax;
+// Traversal state of one ray, kept in registers by a persistent thread.  `step` advances the
+// CWBVH loop by one node visit plus the triangles that visit exposed and returns true when
+// the ray is finished (stack empty, or first accepted triangle for an any-hit ray).
+struct LaneTrav {
+    float ox, oy, oz, dx, dy, dz;
+    float idx, idy, idz;
+    float tmin, tmax;             // tmax shrinks to the closest accepted hit
+    float hu, hv;
+    int htri;                     // position in the leaf-ordered record array, -1 = none
+    uint32_t octinv;
+    uint2 ngroup;
+    bool any_hit;
 
-    hit.tri = -1;
-    hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;
-    stack.sp = 0;
+    __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_,
+                                         float tmin_, float tmax_, bool any_hit_, TravStack& stack) {
+        ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_;
+        idx = safe_rcp_dir(dx_); idy = safe_rcp_dir(dy_); idz = safe_rcp_dir(dz_);
+        tmin = tmin_; tmax = tmax_;
+        hu = 0.f; hv = 0.f; htri = -1;
+        const uint32_t oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
+        octinv = 7u - oct;
+        ngroup = make_uint2(0u, 0x80000000u);      // the root as a one-bit node group
+        any_hit = any_hit_;
+        stack.sp = 0;
+    }
 
-    uint2 ngroup = make_uint2(0u, 0x80000000u);   // the root as a one-bit node group
-    uint2 tgroup = make_uint2(0u, 0u);
-
-    while (true) {
+    __device__ __forceinline__ bool step(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
+                                         TravStack& stack) {
+        uint2 tgroup;
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t bit = 31u - __clz(ngroup.y);
             ngroup.y &= ~(1u << bit);
@@ -201,15 +228,15 @@ __device__ __forceinline__ void traverse(const uint4* __restrict__ nodes,
             const uint32_t node_index = ngroup.x + rel;
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
             uint32_t child_base, tri_base, imask;
-            const uint32_t hm = node_test(nodes, node_index, ray.ox, ray.oy, ray.oz, idx, idy, idz,
-                                          tmin, tmax, octinv4, child_base, tri_base, imask);
+            const uint32_t hm = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
+                                          octinv * 0x01010101u, child_base, tri_base, imask);
             ngroup = make_uint2(child_base, (hm & 0xFF000000u) | imask);
             tgroup = make_uint2(tri_base, hm & 0x00FFFFFFu);
         } else {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);
         }
-
+        const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
         while (tgroup.y != 0u) {
             const uint32_t bit = 31u - __clz(tgroup.y);
             tgroup.y &= ~(1u << bit);
@@ -220,17 +247,16 @@ __device__ __forceinline__ void traverse(const uint4* __restrict__ nodes,
             const float4 rc = __ldg(tp + 2);
             float t, u, v;
             if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
-                hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)ti;
-                tmax = t;
-                if (ANY_HIT) return;
+                tmax = t; hu = u; hv = v; htri = (int)ti;
+                if (any_hit) return true;
             }
         }
-
         if (ngroup.y <= 0x00FFFFFFu) {
-            if (stack.sp == 0) break;
+            if (stack.sp == 0) return true;
             ngroup = stack.pop();
         }
+        return false;
     }
-}
+};
 
 }  // namespace dsrt

@@ -13,9 +13,9 @@ namespace dsrt {
 enum {
     C_NIN = 0,        // rays in the current queue
     C_NOUT = 1,       // rays pushed to the next queue
-    C_NSHADOW = 2,    // shadow rays pushed this bounce
-    C_FETCH_EXT = 3,  // dynamic work counter of the extend kernel
-    C_FETCH_SHD = 4,  // dynamic work counter of the shadow kernel
+    C_NSHADOW0 = 2,   // shadow rays pushed by k_shade at even depth
+    C_NSHADOW1 = 3,   // ... at odd depth (double buffered, see k_advance)
+    C_FETCH = 4,      // dynamic work counter of the traversal kernels
     C_COUNT = 8
 };
 enum { S_PRIMARY = 0, S_BOUNCE = 1, S_SHADOW = 2, S_PATHS = 3, S_COUNT = 4 };
@@ -61,16 +61,15 @@ struct FrameConst {
 };
 
 struct LaunchDims {
-    int extend_blocks = 0, shadow_blocks = 0, shade_blocks = 0;
+    int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0;
 };
 
 // Host-callable launchers (all asynchronous on `s`).
 void launch_dims(LaunchDims* d, int device);
 void launch_batch_begin(const FrameConst& fc, cudaStream_t s);
-void launch_raygen(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
-void launch_extend(const FrameConst& fc, int cur, const LaunchDims& d, cudaStream_t s);
+void launch_primary(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
+void launch_trace(const FrameConst& fc, int cur, int shadow_slot, const LaunchDims& d, cudaStream_t s);
 void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
-void launch_shadow(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_advance(const FrameConst& fc, int depth, cudaStream_t s);
 void launch_resolve(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_tonemap(const float* accum, unsigned char* rgb, int W, int H, float inv_spp, float inv_gamma, cudaStream_t s);

@@ -124,9 +124,10 @@ typedef struct DsrtFrameStats {
     uint32_t kernel_launches;    /* kernels this library launched for the frame */
     uint32_t batches;
     float    device_ms;          /* CUDA-event time of the whole frame on the ctx stream */
-    float    extend_ms;          /* closest-hit traversal kernels only (0 unless stage timing is on) */
-    float    shadow_ms;          /* any-hit traversal kernels only */
-    float    shade_ms;           /* ray-gen + shade + resolve */
+    float    extend_ms;          /* BVH traversal kernels: k_primary + k_trace, closest and any hit
+                                    (0 unless stage timing is on) */
+    float    shadow_ms;          /* 0: shadow rays are traced inside k_trace */
+    float    shade_ms;           /* k_shade */
 } DsrtFrameStats;
 
 #ifdef __cplusplus
