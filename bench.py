@@ -195,6 +195,7 @@ def run_dsrt(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import dsrt_b200 as d
+    from dsrt_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
@@ -216,14 +217,14 @@ def run_dsrt(a, rank, world, local_rank):
     rgb = np.empty((a.height, a.width, 3), np.uint8)
 
     def frame_inputs(i):
-        idx = (i * world + rank) % len(poses) if (world > 1 and a.mode == "frame") else 0
+        # frame-parallel: step i covers frames i*world .. i*world+world-1, rank r takes its own
+        idx = (sharding.frames_of_rank((i + 1) * world, rank, world)[i]) % len(poses) if (world > 1 and a.mode == "frame") else 0
         cam_pos, sun, _ = d.pose_to_model_frame(poses[idx])
         return d.camera_look_at_origin(cam_pos, 40.0, a.width, a.height, a.spp, a.depth), sun
 
     s_lo, s_hi = 0, a.spp
     if world > 1 and a.mode == "sample":
-        s_lo, s_hi = a.spp * rank // world, a.spp * (rank + 1) // world
-        acc_ptr = None
+        s_lo, s_hi = sharding.sample_range(a.spp, rank, world)
 
     def reduce_accum():
         # one NCCL sum-reduce of the float accumulation buffer to rank 0 (NVLink/NVSwitch)
@@ -231,8 +232,7 @@ def run_dsrt(a, rank, world, local_rank):
 
         class _P:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-        t = torch.as_tensor(_P(), device=dev)
-        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        sharding.reduce_accum(torch.as_tensor(_P(), device=dev), dst=0)
 
     def step(i, timed):
         cam, sun = frame_inputs(i)
