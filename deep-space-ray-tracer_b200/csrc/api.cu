@@ -356,6 +356,15 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
     fc.textures = ctx->d_tex;
     fc.texture_pool = ctx->d_pool;
     fc.num_nodes = ctx->bvh.num_nodes;
+    {
+        float ext = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            ext = std::max(ext, ctx->bvh.scene_hi[k] - ctx->bvh.scene_lo[k]);
+            ext = std::max(ext, std::max(std::fabs(ctx->bvh.scene_lo[k]), std::fabs(ctx->bvh.scene_hi[k])));
+        }
+        const float pad = ext * (1.0f / 65536.0f);
+        for (int k = 0; k < 3; ++k) { fc.scene_lo[k] = ctx->bvh.scene_lo[k] - pad; fc.scene_hi[k] = ctx->bvh.scene_hi[k] + pad; }
+    }
     fc.num_textures = ctx->ntex;
     fc.texture_pool_floats = ctx->pool_floats;
 }
@@ -394,7 +403,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     bool fresh = false;
     int rc = ensure_image(ctx, W, H, &fresh);
     if (rc) return rc;
-    if (fresh || (!keep_accum && sample_begin == 0))
+    if (fresh || !keep_accum)
         CK(cudaMemsetAsync(ctx->accum, 0, (size_t)W * H * 3 * sizeof(float), ctx->stream));
 
     const bool full_rect = (x0 == 0 && y0 == 0 && x1 == W && y1 == H);

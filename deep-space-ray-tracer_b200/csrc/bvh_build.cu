@@ -10,8 +10,9 @@
 //   4. binary radix tree, Karras 2012            (k_hierarchy)
 //   5. bottom-up box refit with atomic flags     (k_refit)
 //   6. top-down collapse, one level per launch:  (k_collapse_level)
-//        greedy surface-area expansion of each binary node into <= 8 children,
-//        subtrees of <= 3 triangles become leaf children,
+//        each binary node expands into <= 8 children along the cost-optimal cut found by a
+//        bottom-up dynamic programme over the surface-area heuristic (in k_refit),
+//        subtrees of <= 3 triangles may become leaf children,
 //        children are placed in octant-matched slots,
 //        child boxes are quantised to 8 bits against the node box (conservatively),
 //        nodes are emitted breadth first, triangle records in leaf order.
@@ -168,11 +169,29 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n,
     if (i == 0) parent[0] = -1;
 }
 
-// ---- bottom-up refit --------------------------------------------------------------------
+// ---- bottom-up refit + optimal wide-node assignment ------------------------------------------
+// Besides the boxes, each binary node gets the surface-area cost of representing its subtree
+// with at most i = 1..7 child slots of a wide node, and the decisions that achieve it
+// (dynamic programme of Ylitie et al. 2017, section 4.1, with c_node = 1, c_prim = 0.3):
+//   C(n,1)   = min( A_n * P_n * c_prim  if P_n <= 3          [one leaf child],
+//                   A_n * c_node + D(n,8)                     [a wide node of its own] )
+//   C(n,i)   = min( D(n,i), C(n,i-1) )                        i = 2..7
+//   D(n,j)   = min over 0<k<j of C(left,k) + C(right,j-k)
+// dec packs 3 bits per i: i=1: 0 leaf / 1 wide node; i=2..7: 0 = "use i-1", else k; i=8: k.
+constexpr float kCostNode = 1.0f;
+constexpr float kCostPrim = 0.3f;
+
+__device__ __forceinline__ float box_half_area(float4 l, float4 h) {
+    float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
 __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restrict__ tlo,
                         const float4* __restrict__ thi, int n,
                         const int2* __restrict__ children, const int* __restrict__ parent,
-                        float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags) {
+                        const int2* __restrict__ range,
+                        float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags,
+                        float* __restrict__ cost, uint32_t* __restrict__ dec) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t tri = vals[k];
@@ -180,19 +199,58 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
     int node = n - 1 + k;
     blo[node] = l;
     bhi[node] = h;
+    {
+        const float c = box_half_area(l, h) * kCostPrim;
+        float* cn = cost + (size_t)node * 8;
+        for (int i = 1; i <= 7; ++i) cn[i] = c;
+        dec[node] = 0u;                              // a single triangle is always a leaf child
+    }
     if (n == 1) return;
     int p = parent[node];
     while (p >= 0) {
         __threadfence();
         if (atomicAdd(&flags[p], 1) == 0) return;     // the sibling subtree finishes this node
         int2 ch = children[p];
-        // volatile-style reads through L2: the sibling's stores were fenced before its atomic
         float4 l0 = __ldcg(&blo[ch.x]), h0 = __ldcg(&bhi[ch.x]);
         float4 l1 = __ldcg(&blo[ch.y]), h1 = __ldcg(&bhi[ch.y]);
         l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
         h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
         blo[p] = l;
         bhi[p] = h;
+        // dynamic programme
+        float cl[8], cr[8];
+        for (int i = 1; i <= 7; ++i) {
+            cl[i] = __ldcg(&cost[(size_t)ch.x * 8 + i]);
+            cr[i] = __ldcg(&cost[(size_t)ch.y * 8 + i]);
+        }
+        const float area = box_half_area(l, h);
+        const int2 r = range[p];
+        const int count = r.y - r.x + 1;
+        float dist[9];
+        uint32_t kbest[9];
+        for (int j = 2; j <= 8; ++j) {
+            float best = FLT_MAX;
+            uint32_t bk = 1;
+            for (int kk = 1; kk < j; ++kk) {
+                if (kk > 7 || j - kk > 7) continue;
+                float c = cl[kk] + cr[j - kk];
+                if (c < best) { best = c; bk = (uint32_t)kk; }
+            }
+            dist[j] = best;
+            kbest[j] = bk;
+        }
+        uint32_t d = kbest[8] << 24;
+        float cp[8];
+        const float c_leaf = count <= kMaxLeafTris ? area * (float)count * kCostPrim : FLT_MAX;
+        const float c_wide = area * kCostNode + dist[8];
+        if (c_leaf <= c_wide) { cp[1] = c_leaf; } else { cp[1] = c_wide; d |= 1u << 3; }
+        for (int i = 2; i <= 7; ++i) {
+            if (dist[i] < cp[i - 1]) { cp[i] = dist[i]; d |= kbest[i] << (3 * i); }
+            else cp[i] = cp[i - 1];
+        }
+        float* cn = cost + (size_t)p * 8;
+        for (int i = 1; i <= 7; ++i) cn[i] = cp[i];
+        dec[p] = d;
         p = parent[p];
     }
 }
@@ -204,6 +262,7 @@ struct CollapseArgs {
     const int2* range;
     const float4* blo;
     const float4* bhi;
+    const uint32_t* dec;           // per binary node: decisions of the dynamic programme (k_refit)
     const uint32_t* vals;          // sorted position -> original triangle index
     const DsrtTriangle* tris;      // raw triangles (device copy)
     uint4* nodes;                  // out
@@ -233,26 +292,41 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
     const int wnode = items_in[it].y;
     const int n = A.n;
 
+    // Children of this wide node: follow the decisions of the dynamic programme.  `leafbits`
+    // marks the children that are leaf clusters; the others become wide nodes themselves.
     int ch[8];
-    int nch;
-    if (subtree_count(A, bnode) <= kMaxLeafTris) {     // whole scene fits one leaf (n <= 3)
-        ch[0] = bnode; nch = 1;
-    } else {
-        int2 c = A.children[bnode];
-        ch[0] = c.x; ch[1] = c.y; nch = 2;
-        while (nch < 8) {
-            int best = -1;
-            float best_area = -1.f;
-            for (int k = 0; k < nch; ++k) {
-                int c2 = ch[k];
-                if (subtree_count(A, c2) <= kMaxLeafTris) continue;
-                float a = half_area(A.blo[c2], A.bhi[c2]);
-                if (a > best_area) { best_area = a; best = k; }
+    int nch = 0;
+    uint32_t leafbits = 0;
+    {
+        const bool root_is_leaf = bnode >= n - 1 || ((A.dec[bnode] >> 3) & 7u) == 0u;
+        if (root_is_leaf) {                       // the whole scene fits one leaf child (n <= 3)
+            ch[0] = bnode; nch = 1; leafbits = 1u;
+        } else {
+            int st_node[16], st_slots[16];
+            int sp = 0;
+            st_node[sp] = bnode; st_slots[sp] = 8; ++sp;          // distribute bnode's children over 8 slots
+            bool first = true;
+            while (sp > 0) {
+                --sp;
+                int c = st_node[sp], i = st_slots[sp];
+                if (!first) {
+                    // represent subtree c with at most i slots
+                    const uint32_t d = c >= n - 1 ? 0u : A.dec[c];
+                    while (i > 1 && ((d >> (3 * i)) & 7u) == 0u) --i;
+                    if (i == 1 || c >= n - 1) {
+                        const bool leaf = c >= n - 1 || ((d >> 3) & 7u) == 0u;
+                        if (leaf) leafbits |= 1u << nch;
+                        ch[nch++] = c;
+                        continue;
+                    }
+                }
+                first = false;
+                const uint32_t d = A.dec[c];
+                const int k = (int)((d >> (3 * i)) & 7u);
+                const int2 cc = A.children[c];
+                st_node[sp] = cc.y; st_slots[sp] = i - k; ++sp;
+                st_node[sp] = cc.x; st_slots[sp] = k; ++sp;
             }
-            if (best < 0) break;
-            int2 cc = A.children[ch[best]];
-            ch[best] = cc.x;
-            ch[nch++] = cc.y;
         }
     }
 
@@ -295,8 +369,7 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
     for (int s = 0; s < 8; ++s) {
         int k = slot_child[s];
         if (k < 0) continue;
-        int cnt = subtree_count(A, ch[k]);
-        if (cnt <= kMaxLeafTris) n_tris += cnt;
+        if ((leafbits >> k) & 1u) n_tris += subtree_count(A, ch[k]);
         else { imask |= 1u << s; ++n_inner; }
     }
     uint32_t child_base = 0, tri_base = 0, item_base = 0;
@@ -347,7 +420,7 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
         }
         int node_c = ch[k];
         int cnt = subtree_count(A, node_c);
-        if (cnt <= kMaxLeafTris) {
+        if ((leafbits >> k) & 1u) {
             int first = node_c >= n - 1 ? node_c - (n - 1) : A.range[node_c].x;
             for (int j = 0; j < cnt; ++j) {
                 uint32_t tri = A.vals[first + j];
@@ -416,6 +489,8 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     uint64_t *keys = nullptr, *keys_s = nullptr;
     int2 *children = nullptr, *range = nullptr, *items[2] = {nullptr, nullptr};
     int *parent = nullptr, *flags = nullptr;
+    float* cost = nullptr;
+    uint32_t* dec = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -445,6 +520,8 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     DSRT_CUDA(cudaMalloc(&flags, sizeof(int) * (size_t)n));
     DSRT_CUDA(cudaMalloc(&blo, sizeof(float4) * (size_t)(2 * n)));
     DSRT_CUDA(cudaMalloc(&bhi, sizeof(float4) * (size_t)(2 * n)));
+    DSRT_CUDA(cudaMalloc(&cost, sizeof(float) * 8 * (size_t)(2 * n)));
+    DSRT_CUDA(cudaMalloc(&dec, sizeof(uint32_t) * (size_t)(2 * n)));
     DSRT_CUDA(cudaMalloc(&counters, sizeof(uint32_t) * 4));
     DSRT_CUDA(cudaMalloc(&items[0], sizeof(int2) * (size_t)n));
     DSRT_CUDA(cudaMalloc(&items[1], sizeof(int2) * (size_t)n));
@@ -460,7 +537,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
 
     DSRT_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
     if (n > 1) k_hierarchy<<<(n - 1 + TB - 1) / TB, TB, 0, stream>>>(keys_s, n, children, parent, range);
-    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, blo, bhi, flags);
+    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, range, blo, bhi, flags, cost, dec);
     DSRT_CUDA(cudaGetLastError());
 
     DSRT_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, stream));
@@ -486,7 +563,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
         if (!(ext > 0.f)) ext = 1.f;
         CollapseArgs A;
         A.n = n; A.children = children; A.range = range; A.blo = blo; A.bhi = bhi;
-        A.vals = vals_s; A.tris = d_tris; A.nodes = B.nodes; A.tri_records = B.tri_records;
+        A.dec = dec; A.vals = vals_s; A.tris = d_tris; A.nodes = B.nodes; A.tri_records = B.tri_records;
         A.counters = counters;
         A.eps = ext * (1.0f / 524288.0f);         // 2^-19 of the scene size
         {
@@ -532,7 +609,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
 
     cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
     cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
-    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters);
+    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters); cudaFree(cost); cudaFree(dec);
     cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     *out = B;
@@ -541,7 +618,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
 fail:
     cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
     cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
-    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters);
+    cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters); cudaFree(cost); cudaFree(dec);
     cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);

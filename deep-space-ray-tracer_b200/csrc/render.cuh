@@ -33,6 +33,7 @@ struct FrameConst {
     const DsrtTextureHeader* textures;
     const float* texture_pool;
     int num_nodes, num_textures, texture_pool_floats;
+    float scene_lo[3], scene_hi[3];   // scene bounds padded by 2^-16 of the scene size (root-box test)
     // camera (reference GPUCamera fields that the kernel reads)
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
     int W, H;

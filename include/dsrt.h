@@ -78,8 +78,8 @@ int dsrt_scene_download(dsrt_ctx* ctx, void* nodes, size_t node_bytes, void* tri
  * Renders samples [sample_begin, sample_end) of every pixel of `rect` (x0,y0,x1,y1, half
  * open, y = 0 is the bottom row as in the reference; NULL = whole image) and ADDS the
  * per-sample clamped radiance into the ctx's float accumulation buffer (W*H*3, pixel-major,
- * row 0 = bottom).  The buffer is zeroed when sample_begin == 0 or the image size changes,
- * unless `keep_accum` is non-zero.  params->samples_per_pixel is the frame's total spp
+ * row 0 = bottom).  The buffer is zeroed first unless `keep_accum` is non-zero (progressive
+ * refinement: later sample ranges of the same frame pass keep_accum = 1).  params->samples_per_pixel is the frame's total spp
  * (the sample jitter divides by it); max_depth, gamma and rng_mode are honoured, the other
  * fields are carried but unused, exactly as in the reference kernel.
  *

@@ -148,6 +148,13 @@ def test_sample_sharding_rect_and_determinism(dsrt, poses, ctx):
     ctx.render(cam, sun, params, sample_begin=0, sample_end=5)
     ctx.render(cam, sun, params, sample_begin=5, sample_end=spp, keep_accum=True)
     assert np.allclose(ctx.readback_accum(), full, atol=1e-5)
+    # a shard that does not start at sample 0 is zeroed too unless keep_accum is set
+    ctx.render(cam, sun, params, sample_begin=5, sample_end=spp)
+    tail = ctx.readback_accum()
+    ctx.render(cam, sun, params, sample_begin=5, sample_end=spp)
+    assert np.array_equal(ctx.readback_accum(), tail)
+    ctx.render(cam, sun, params, sample_begin=0, sample_end=5)
+    assert np.allclose(ctx.readback_accum() + tail, full, atol=1e-5)
     # batch size does not change the result
     ctx.set_samples_per_batch(3)
     ctx.render(cam, sun, params)
