@@ -217,9 +217,8 @@ struct LaneTrav {
         stack.sp = 0;
     }
 
-    // One node visit.  Afterwards `tgroup` holds the triangles that visit exposed (or a
-    // postponed triangle group popped from the stack).
-    __device__ __forceinline__ uint2 node_phase(const uint4* __restrict__ nodes, TravStack& stack) {
+    __device__ __forceinline__ bool step(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
+                                         TravStack& stack) {
         uint2 tgroup;
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t bit = 31u - __clz(ngroup.y);
@@ -237,11 +236,6 @@ struct LaneTrav {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);
         }
-        return tgroup;
-    }
-
-    // Tests the triangles of `tgroup`; returns true when an any-hit ray found its hit.
-    __device__ __forceinline__ bool tri_phase(const float4* __restrict__ tris, uint2 tgroup) {
         const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
         while (tgroup.y != 0u) {
             const uint32_t bit = 31u - __clz(tgroup.y);
@@ -257,12 +251,6 @@ struct LaneTrav {
                 if (any_hit) return true;
             }
         }
-        return false;
-    }
-
-    // Takes the next node group from the stack when the current one is exhausted; returns
-    // true when the ray is finished.
-    __device__ __forceinline__ bool pop_phase(TravStack& stack) {
         if (ngroup.y <= 0x00FFFFFFu) {
             if (stack.sp == 0) return true;
             ngroup = stack.pop();
