@@ -255,13 +255,15 @@ def run_dsrt(a, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms = rays = launches = ext_ms = ext_rays = 0.0
+    ms = rays = launches = ext_ms = ext_rays = prim_ms = shade_ms = 0.0
     for i in range(a.steps):
         m, fs = step(a.warmup + i, True)
         ms += m
         rays += fs.rays
         launches += fs.kernel_launches
         ext_ms += fs.extend_ms
+        prim_ms += fs.primary_ms
+        shade_ms += fs.shade_ms
         ext_rays += fs.rays
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -323,7 +325,8 @@ def run_dsrt(a, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "k_primary + k_trace (BVH8 traversal, closest and any hit)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_ray": bpr, "rays_per_step": ext_rays / world / a.steps,
-                         "kernel_ms_per_step": ext_ms / a.steps, "traffic": traffic},
+                         "kernel_ms_per_step": ext_ms / a.steps, "k_primary_ms_per_step": prim_ms / a.steps,
+                         "k_shade_ms_per_step": shade_ms / a.steps, "traffic": traffic},
         }
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, tris, mats, poses)

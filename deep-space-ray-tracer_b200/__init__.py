@@ -77,7 +77,7 @@ class SceneStats(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("paths", C.c_uint64), ("kernel_launches", C.c_uint32), ("batches", C.c_uint32),
-                ("device_ms", C.c_float), ("extend_ms", C.c_float), ("shadow_ms", C.c_float),
+                ("device_ms", C.c_float), ("extend_ms", C.c_float), ("primary_ms", C.c_float),
                 ("shade_ms", C.c_float)]
 
     @property

@@ -188,6 +188,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     ctx->device = device;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->counters, sizeof(uint32_t) * C_COUNT) == cudaSuccess &&
+              cudaMemset(ctx->counters, 0, sizeof(uint32_t) * C_COUNT) == cudaSuccess &&
               cudaMalloc(&ctx->stats, sizeof(unsigned long long) * S_COUNT) == cudaSuccess &&
               cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_frame[0]) == cudaSuccess &&
@@ -465,7 +466,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
 
     uint32_t launches = 0, batches = 0;
     size_t nev = 0;                 // events used from the pool
-    std::vector<int> ev_kind;       // what the interval [k, k+1) measured: 0 traversal, 1 shade, -1 other
+    std::vector<int> ev_kind;       // what the interval [k, k+1) measured: 0 k_trace, 1 k_shade, 2 k_primary, -1 other
     const bool timing = ctx->stage_timing != 0;
     auto mark = [&](int kind_of_next_interval) {
         if (!timing || nev >= (size_t)kMaxEvents) return;
@@ -480,7 +481,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
         fc.s0 = s0;
         fc.spb = std::min(spb, sample_end - s0);
         launch_batch_begin(fc, ctx->stream);
-        mark(0);
+        mark(2);
         launch_primary(fc, ctx->dims, ctx->stream);
         launches += 2;
         int cur = 0;
@@ -521,14 +522,15 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     fs.batches = batches;
     cudaEventElapsedTime(&fs.device_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
     if (timing) {
-        float trav = 0.f, shade = 0.f;
+        float trav = 0.f, shade = 0.f, prim = 0.f;
         for (size_t k = 0; k + 1 < nev; ++k) {
             float ms = 0.f;
             if (ev_kind[k] < 0) continue;
             cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-            if (ev_kind[k] == 0) trav += ms; else shade += ms;
+            if (ev_kind[k] == 1) shade += ms; else trav += ms;
+            if (ev_kind[k] == 2) prim += ms;
         }
-        fs.extend_ms = trav; fs.shadow_ms = 0.f; fs.shade_ms = shade;
+        fs.extend_ms = trav; fs.primary_ms = prim; fs.shade_ms = shade;
     }
     ctx->fstats = fs;
     return DSRT_OK;

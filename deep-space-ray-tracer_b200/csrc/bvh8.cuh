@@ -88,11 +88,13 @@ __device__ __forceinline__ bool tri_test(const float4 ra, const float4 rb, const
     const V3 e2 = v3(rc.x, rc.y, rc.z);
     const V3 pvec = vcross(dir, e2);
     const float det = vdot(e1, pvec);
-    if (fabsf(det) < 1e-8f) return false;
+    // The |det| and u rejections share one branch: both need nothing but arithmetic, and a
+    // separate early-out on det lets the compiler sink the v0 load below it, which serialises two
+    // memory latencies per test (profiles/r01_c).  Same accept set as the reference's two tests.
     const float inv = __frcp_rn(det);
     const V3 tvec = vsub(orig, v0);
     const float u = __fmul_rn(vdot(tvec, pvec), inv);
-    if (u < 0.0f || u > 1.0f) return false;
+    if (fabsf(det) < 1e-8f || u < 0.0f || u > 1.0f) return false;
     const V3 qvec = vcross(tvec, e1);
     const float v = __fmul_rn(vdot(dir, qvec), inv);
     if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
@@ -102,33 +104,63 @@ __device__ __forceinline__ bool tri_test(const float4 ra, const float4 rb, const
     return true;
 }
 
+// The three 128-bit loads of a triangle record, issued together.  Written as volatile asm
+// because the compiler otherwise sinks the v0 load below the |det| early-out of tri_test, which
+// puts a second full memory latency into every triangle test (profiles/r01_c: the triangle loop
+// is 21 % of the traversal instructions but 41 % of its stall samples).
+__device__ __forceinline__ void load_tri_record(const float4* tp, float4& ra, float4& rb, float4& rc) {
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(ra.x), "=f"(ra.y), "=f"(ra.z), "=f"(ra.w) : "l"(tp));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4+16];"
+                 : "=f"(rb.x), "=f"(rb.y), "=f"(rb.z), "=f"(rb.w) : "l"(tp));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4+32];"
+                 : "=f"(rc.x), "=f"(rc.y), "=f"(rc.z), "=f"(rc.w) : "l"(tp));
+}
+
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     // each byte: 0x80 set -> 0xFF, else 0x00
     return ((x >> 7) & 0x01010101u) * 0xFFu;
 }
 
-// Byte j of a packed word as a float.  I2F.U8 runs on the XU pipe (16 lanes/clk/SM) and 48 of
-// them per node visit saturate it (profiles/r01_a: XU 81 % busy).  The alternative builds the
-// float 2^23 + byte with one PRMT (ALU pipe) and subtracts 2^23 with one FADD (FMA pipe):
-// exact, and spread over the two wide pipes.  kI2fMask picks, per plane set (near x,y,z, far
-// x,y,z = bits 0..5), which conversion is used so the three pipes can be balanced.
-template <bool USE_I2F>
-__device__ __forceinline__ float byte_to_float(uint32_t w, int j) {
-    if (USE_I2F) return (float)((w >> (8 * j)) & 0xFFu);
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)j)) - 8388608.0f;
+// Byte j of a packed plane word as the float 1 + q * 2^-15: one PRMT drops the byte into
+// mantissa bits 8..15 of 1.0f (0x3F800000).  `one` must live in a register so that the PRMT
+// selector can be the instruction's immediate; the caller gets it from memory the compiler
+// cannot see through.  (profiles/r01_c: I2F.U8 is a quarter-rate XU instruction, and the earlier
+// PRMT + FADD(-2^23) form cost two instructions per plane plus a register move for every selector.)
+template <int J>
+__device__ __forceinline__ float plane_byte(uint32_t w, uint32_t one) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
 }
 
-#ifndef DSRT_I2F_MASK
-#define DSRT_I2F_MASK 0x09      // near-x and far-x through I2F, the other four through PRMT+FADD
-#endif
-constexpr int kI2fMask = DSRT_I2F_MASK;
+// Slab constants of one axis for the folded form  t = fma(1 + q*2^-15, A, B):
+//   A  = 2^15 * step * (1/d)               (exact: a power-of-two scaling of 1/d)
+//   B0 = b - A * (1 + s*2^-22)             near planes, s = sign(A)
+//   B1 = b - A * (1 - s*2^-22)             far planes,  b = (p - o) * (1/d)
+// B carries a rounding error of 2^-24 |B| <= 2^-24 (|b| + |A|): the |A| part is 2^-9 of one
+// quantisation step in t, which the 2^-22 |A| bias (2^-7 of a step, towards "box larger")
+// over-covers; the |b| part is of the size the builder's box padding already absorbs.
+struct SlabAxis { float A, B0, A1, B1; };
+__device__ __forceinline__ SlabAxis slab_axis(uint32_t ebyte, float p, float o, float id) {
+    constexpr float kWiden = 1.0f + 9.5367431640625e-07f;      // far planes: 2^-20 relative, as before
+    constexpr float kUp = 1.0f + 2.384185791015625e-07f, kDown = 1.0f - 2.384185791015625e-07f;   // 1 +- 2^-22
+    SlabAxis s;
+    s.A = __uint_as_float((ebyte << 23) + 0x07800000u) * id;
+    const float b = (p - o) * id;
+    const bool neg = id < 0.0f;
+    s.B0 = fmaf(-s.A, neg ? kDown : kUp, b);
+    s.B1 = fmaf(-s.A, neg ? kUp : kDown, b) * kWiden;
+    s.A1 = s.A * kWiden;
+    return s;
+}
 
 // Intersects the eight child boxes of one node; returns the hit mask (bits 24..31 inner
 // children in traversal-priority order, bits 0..23 triangles).
 __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, uint32_t node_index,
                                               float ox, float oy, float oz,
                                               float idx, float idy, float idz,
-                                              float tmin, float tmax, uint32_t octinv4,
+                                              float tmin, float tmax, uint32_t octinv4, uint32_t one,
                                               uint32_t& child_base, uint32_t& tri_base, uint32_t& imask) {
     const uint4* np = nodes + (size_t)node_index * kNodeWords;
     const uint4 w0 = __ldg(np + 0);
@@ -137,23 +169,14 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
     const uint4 w3 = __ldg(np + 3);
     const uint4 w4 = __ldg(np + 4);
 
-    const float px = __uint_as_float(w0.x), py = __uint_as_float(w0.y), pz = __uint_as_float(w0.z);
     const uint32_t ew = w0.w;
     imask = ew >> 24;
     child_base = w1.x;
     tri_base = w1.y;
 
-    const float ax = __uint_as_float((ew & 0xFFu) << 23) * idx;
-    const float ay = __uint_as_float(((ew >> 8) & 0xFFu) << 23) * idy;
-    const float az = __uint_as_float(((ew >> 16) & 0xFFu) << 23) * idz;
-    const float bx = (px - ox) * idx;
-    const float by = (py - oy) * idy;
-    const float bz = (pz - oz) * idz;
-    // far planes widened by 2^-20 (relative): the slab test must never reject what the exact
-    // triangle test accepts, whatever the distance between ray origin and node.
-    constexpr float kWiden = 1.0f + 9.5367431640625e-07f;
-    const float ax1 = ax * kWiden, ay1 = ay * kWiden, az1 = az * kWiden;
-    const float bx1 = bx * kWiden, by1 = by * kWiden, bz1 = bz * kWiden;
+    const SlabAxis X = slab_axis(ew & 0xFFu, __uint_as_float(w0.x), ox, idx);
+    const SlabAxis Y = slab_axis((ew >> 8) & 0xFFu, __uint_as_float(w0.y), oy, idy);
+    const SlabAxis Z = slab_axis((ew >> 16) & 0xFFu, __uint_as_float(w0.z), oz, idz);
 
     uint32_t hitmask = 0;
 #pragma unroll
@@ -170,23 +193,24 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
         const uint32_t nx = idx < 0.0f ? qhix : qlox, fx = idx < 0.0f ? qlox : qhix;
         const uint32_t ny = idy < 0.0f ? qhiy : qloy, fy = idy < 0.0f ? qloy : qhiy;
         const uint32_t nz = idz < 0.0f ? qhiz : qloz, fz = idz < 0.0f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int sh = 8 * j;
-            const float t0x = fmaf(byte_to_float<(kI2fMask & 1) != 0>(nx, j), ax, bx);
-            const float t0y = fmaf(byte_to_float<(kI2fMask & 2) != 0>(ny, j), ay, by);
-            const float t0z = fmaf(byte_to_float<(kI2fMask & 4) != 0>(nz, j), az, bz);
-            const float t1x = fmaf(byte_to_float<(kI2fMask & 8) != 0>(fx, j), ax1, bx1);
-            const float t1y = fmaf(byte_to_float<(kI2fMask & 16) != 0>(fy, j), ay1, by1);
-            const float t1z = fmaf(byte_to_float<(kI2fMask & 32) != 0>(fz, j), az1, bz1);
-            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-            if (cmin <= cmax) {
-                const uint32_t bits = (child_bits4 >> sh) & 0xFFu;
-                const uint32_t idxb = (bit_index4 >> sh) & 0xFFu;
-                hitmask |= bits << idxb;
-            }
+#define DSRT_CHILD(J)                                                                      \
+        {                                                                                  \
+            const float t0x = fmaf(plane_byte<J>(nx, one), X.A, X.B0);                     \
+            const float t0y = fmaf(plane_byte<J>(ny, one), Y.A, Y.B0);                     \
+            const float t0z = fmaf(plane_byte<J>(nz, one), Z.A, Z.B0);                     \
+            const float t1x = fmaf(plane_byte<J>(fx, one), X.A1, X.B1);                    \
+            const float t1y = fmaf(plane_byte<J>(fy, one), Y.A1, Y.B1);                    \
+            const float t1z = fmaf(plane_byte<J>(fz, one), Z.A1, Z.B1);                    \
+            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                   \
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                   \
+            if (cmin <= cmax) {                                                            \
+                const uint32_t bits = (child_bits4 >> (8 * J)) & 0xFFu;                    \
+                const uint32_t idxb = (bit_index4 >> (8 * J)) & 0xFFu;                     \
+                hitmask |= bits << idxb;                                                   \
+            }                                                                              \
         }
+        DSRT_CHILD(0) DSRT_CHILD(1) DSRT_CHILD(2) DSRT_CHILD(3)
+#undef DSRT_CHILD
     }
     return hitmask;
 }
@@ -202,6 +226,7 @@ struct LaneTrav {
     int htri;                     // position in the leaf-ordered record array, -1 = none
     uint32_t octinv;
     uint2 ngroup;
+    uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
     bool any_hit;
 
     __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_,
@@ -229,7 +254,7 @@ struct LaneTrav {
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
             uint32_t child_base, tri_base, imask;
             const uint32_t hm = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
-                                          octinv * 0x01010101u, child_base, tri_base, imask);
+                                          octinv * 0x01010101u, one, child_base, tri_base, imask);
             ngroup = make_uint2(child_base, (hm & 0xFF000000u) | imask);
             tgroup = make_uint2(tri_base, hm & 0x00FFFFFFu);
         } else {
@@ -242,9 +267,8 @@ struct LaneTrav {
             tgroup.y &= ~(1u << bit);
             const uint32_t ti = tgroup.x + bit;
             const float4* tp = tris + (size_t)ti * kTriWords;
-            const float4 ra = __ldg(tp + 0);
-            const float4 rb = __ldg(tp + 1);
-            const float4 rc = __ldg(tp + 2);
+            float4 ra, rb, rc;
+            load_tri_record(tp, ra, rb, rc);
             float t, u, v;
             if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
                 tmax = t; hu = u; hv = v; htri = (int)ti;

@@ -16,6 +16,7 @@ enum {
     C_NSHADOW0 = 2,   // shadow rays pushed by k_shade at even depth
     C_NSHADOW1 = 3,   // ... at odd depth (double buffered, see k_advance)
     C_FETCH = 4,      // dynamic work counter of the traversal kernels
+    C_ZERO = 7,       // always 0 (an opaque zero for the traversal kernels, see trace_loop)
     C_COUNT = 8
 };
 enum { S_PRIMARY = 0, S_BOUNCE = 1, S_SHADOW = 2, S_PATHS = 3, S_COUNT = 4 };

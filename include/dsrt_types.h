@@ -126,7 +126,8 @@ typedef struct DsrtFrameStats {
     float    device_ms;          /* CUDA-event time of the whole frame on the ctx stream */
     float    extend_ms;          /* BVH traversal kernels: k_primary + k_trace, closest and any hit
                                     (0 unless stage timing is on) */
-    float    shadow_ms;          /* 0: shadow rays are traced inside k_trace */
+    float    primary_ms;         /* k_primary alone (included in extend_ms; the sun shadow rays are
+                                    traced inside k_trace and have no time of their own) */
     float    shade_ms;           /* k_shade */
 } DsrtFrameStats;
 

@@ -204,7 +204,7 @@ def main():
             fs = c2.render(cm, sun, params)
             out[f"run{it}"] = dict(device_ms=fs.device_ms, rays=int(fs.rays), primary=int(fs.primary_rays), bounce=int(fs.bounce_rays),
                                    shadow=int(fs.shadow_rays), mrays_s=fs.rays / fs.device_ms / 1e3, extend_ms=fs.extend_ms,
-                                   shadow_ms=fs.shadow_ms, shade_ms=fs.shade_ms, launches=fs.kernel_launches, batches=fs.batches)
+                                   primary_ms=fs.primary_ms, shade_ms=fs.shade_ms, launches=fs.kernel_launches, batches=fs.batches)
         img = c2.readback_rgb8(spp, 2.0)
         d.write_png(OUT / "probe_1m.png", img, w, h)
         c2.close()
