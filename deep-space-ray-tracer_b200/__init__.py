@@ -43,7 +43,10 @@ material_dtype = np.dtype(
     [("type", "<i4"), ("albedo_tex", "<i4"), ("pad0", "<i4"), ("pad1", "<i4"),
      ("albedo", vec3), ("emissive", vec3), ("fuzz", "<f4"), ("ref_idx", "<f4")]
 )
+sphere_dtype = np.dtype([("center", vec3), ("radius", "<f4"), ("material_id", "<i4"), ("pad", "<i4")])
+texture_header_dtype = np.dtype([("width", "<i4"), ("height", "<i4"), ("offset", "<i4")])
 assert triangle_dtype.itemsize == 116 and material_dtype.itemsize == 48
+assert sphere_dtype.itemsize == 24 and texture_header_dtype.itemsize == 12
 
 
 class Vec3(C.Structure):
@@ -96,7 +99,8 @@ SYMBOLS = [
     "dsrt_trace_closest", "dsrt_trace_occluded", "dsrt_first_hits",
     "dsrt_trace_closest_device", "dsrt_trace_occluded_device",
     "dsrt_read_pose_file", "dsrt_pose_to_model_frame", "dsrt_camera_look_at_origin",
-    "dsrt_synth_mesh", "dsrt_write_ppm", "dsrt_write_png", "dsrt_version",
+    "dsrt_synth_mesh", "dsrt_mesh_load_obj", "dsrt_mesh_view", "dsrt_mesh_free",
+    "dsrt_write_ppm", "dsrt_write_png", "dsrt_version",
     "gpu_render_scene",
 ]
 
@@ -132,6 +136,10 @@ lib.dsrt_pose_to_model_frame.restype = None
 lib.dsrt_camera_look_at_origin.argtypes = [_vp, _f, _i, _i, _i, _i, C.POINTER(Camera)]
 lib.dsrt_camera_look_at_origin.restype = None
 lib.dsrt_synth_mesh.argtypes = [_i, C.c_uint32, _i, _vp, _vp, _i]
+lib.dsrt_mesh_load_obj.argtypes = [C.c_char_p, C.c_double, C.POINTER(_vp)]
+lib.dsrt_mesh_view.argtypes = [_vp, _vp]
+lib.dsrt_mesh_free.argtypes = [_vp]
+lib.dsrt_mesh_free.restype = None
 lib.dsrt_write_ppm.argtypes = [C.c_char_p, _vp, _i, _i]
 lib.dsrt_write_png.argtypes = [C.c_char_p, _vp, _i, _i]
 lib.dsrt_version.restype = C.c_char_p
@@ -188,6 +196,40 @@ def synth_mesh(ntris: int, seed: int = 1337, diffuse_only: bool = False):
     return tris, mats[:nm].copy()
 
 
+class MeshView(C.Structure):
+    _fields_ = [("triangles", _vp), ("num_triangles", C.c_int32), ("materials", _vp), ("num_materials", C.c_int32),
+                ("textures", _vp), ("num_textures", C.c_int32), ("texture_pool", _vp), ("texture_pool_floats", C.c_int32),
+                ("num_vertices", C.c_int32), ("num_uvs", C.c_int32), ("skipped_faces", C.c_int32),
+                ("textures_failed", C.c_int32), ("textures_flipped", C.c_int32)]
+
+
+def load_obj(path, scale: float = 1.0) -> dict:
+    """OBJ + MTL + map_Kd textures through dsrt_mesh_load_obj (host/obj_loader.cpp): dict with
+    the structured arrays `tris`, `mats`, `textures`, the float `texture_pool` and the counters."""
+    h = _vp()
+    rc = lib.dsrt_mesh_load_obj(os.fsencode(str(path)), float(scale), C.byref(h))
+    if rc != OK:
+        raise DsrtError(f"cannot load OBJ {path} ({rc})")
+    try:
+        v = MeshView()
+        lib.dsrt_mesh_view(h, C.byref(v))
+
+        def grab(ptr, n, dtype):
+            if not n:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+        return {"tris": grab(v.triangles, v.num_triangles, triangle_dtype),
+                "mats": grab(v.materials, v.num_materials, material_dtype),
+                "textures": grab(v.textures, v.num_textures, texture_header_dtype),
+                "texture_pool": grab(v.texture_pool, v.texture_pool_floats, np.float32),
+                "num_vertices": v.num_vertices, "num_uvs": v.num_uvs, "skipped_faces": v.skipped_faces,
+                "textures_failed": v.textures_failed, "textures_flipped": bool(v.textures_flipped)}
+    finally:
+        lib.dsrt_mesh_free(h)
+
+
 def make_params(width, height, spp, max_depth, rng_mode=RNG_PHILOX, gamma=2.0) -> RenderParams:
     p = RenderParams()
     p.img_width, p.img_height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
@@ -240,10 +282,19 @@ class Context:
     def stream(self) -> int:
         return lib.dsrt_stream(self._h) or 0
 
-    def upload_scene(self, tris: np.ndarray, mats: np.ndarray) -> SceneStats:
+    def upload_scene(self, tris: np.ndarray, mats: np.ndarray, spheres: np.ndarray | None = None,
+                     textures: np.ndarray | None = None, texture_pool: np.ndarray | None = None) -> SceneStats:
+        """tris/mats/spheres/textures: structured arrays in the reference's GPUScene layouts;
+        texture_pool: float32 RGB pool the texture headers index (gpu_scene.h:28-32)."""
         t = np.ascontiguousarray(tris, dtype=triangle_dtype)
         m = np.ascontiguousarray(mats, dtype=material_dtype)
-        self._ck(lib.dsrt_scene_upload(self._h, t.ctypes.data, len(t), m.ctypes.data, len(m), None, 0, None, 0, None, 0))
+        sp = np.ascontiguousarray(spheres if spheres is not None else [], dtype=sphere_dtype)
+        th = np.ascontiguousarray(textures if textures is not None else [], dtype=texture_header_dtype)
+        tp = np.ascontiguousarray(texture_pool if texture_pool is not None else [], dtype=np.float32)
+        self._ck(lib.dsrt_scene_upload(self._h, t.ctypes.data if len(t) else None, len(t), m.ctypes.data, len(m),
+                                       sp.ctypes.data if len(sp) else None, len(sp),
+                                       th.ctypes.data if len(th) else None, len(th),
+                                       tp.ctypes.data if len(tp) else None, len(tp)))
         return self.scene_stats()
 
     def upload_scene_device(self, tris_ptr: int, ntris: int, mats_ptr: int, nmats: int) -> SceneStats:

@@ -43,6 +43,9 @@ struct dsrt_ctx {
     DsrtTextureHeader* d_tex = nullptr;
     float* d_pool = nullptr;
     int ntex = 0, pool_floats = 0;
+    float4* d_spheres = nullptr;       // 2 x float4 per sphere (render.cuh)
+    int* d_sphere_lights = nullptr;
+    int nspheres = 0, nsphere_lights = 0;
     DsrtSceneStats sstats{};
 
     // frame
@@ -95,7 +98,9 @@ void free_scene(dsrt_ctx* c) {
     cudaFree(c->d_mats); c->d_mats = nullptr;
     cudaFree(c->d_tex); c->d_tex = nullptr;
     cudaFree(c->d_pool); c->d_pool = nullptr;
-    c->nmats = c->ntex = c->pool_floats = 0;
+    cudaFree(c->d_spheres); c->d_spheres = nullptr;
+    cudaFree(c->d_sphere_lights); c->d_sphere_lights = nullptr;
+    c->nmats = c->ntex = c->pool_floats = c->nspheres = c->nsphere_lights = 0;
     c->have_scene = false;
 }
 
@@ -226,14 +231,18 @@ namespace {
 // Common tail of the two upload entry points.  `tris`/`mats`/`textures`/`pool` are host
 // pointers when from_device is false and device pointers (on ctx's GPU) when it is true.
 int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris, int ntris,
-                      const DsrtMaterial* mats, int nmats, int nspheres,
+                      const DsrtMaterial* mats, int nmats, const DsrtSphere* spheres, int nspheres,
                       const DsrtTextureHeader* textures, int ntextures,
                       const float* texture_pool, int texture_pool_floats) {
     if (ntris < 0 || nmats < 0 || (ntris > 0 && !tris) || (nmats > 0 && !mats))
         return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad triangle/material arguments");
-    if (ntris > 0 && nmats == 0) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: triangles without materials");
-    if (nspheres > 0)
-        return fail(ctx, DSRT_EUNSUPPORTED, "spheres are not built yet (the reference's main() never creates any)");
+    if ((ntris > 0 || nspheres > 0) && nmats == 0) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: geometry without materials");
+    if (nspheres < 0 || (nspheres > 0 && !spheres)) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad sphere arguments");
+    if (nspheres > 0 && from_device)
+        return fail(ctx, DSRT_EUNSUPPORTED, "dsrt_scene_upload_device takes no spheres (they are packed on the host)");
+    for (int i = 0; i < nspheres; ++i)
+        if (spheres[i].material_id < 0 || spheres[i].material_id >= nmats)
+            return fail(ctx, DSRT_EINVAL, "sphere %d has material_id %d outside [0,%d)", i, spheres[i].material_id, nmats);
     if (ntextures < 0 || (ntextures > 0 && (!textures || !texture_pool || texture_pool_floats <= 0)))
         return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad texture arguments");
     if (!from_device)
@@ -261,6 +270,31 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
         CK(cudaMemcpyAsync(ctx->d_pool, texture_pool, sizeof(float) * (size_t)texture_pool_floats, kind, ctx->stream));
         ctx->ntex = ntextures;
         ctx->pool_floats = texture_pool_floats;
+    }
+    if (nspheres > 0) {
+        // Sphere records for the brute-force loop of scene_hit (gpu_render.cu:530-546) and the list
+        // of emissive spheres that ray_color rebuilds at every diffuse hit (gpu_render.cu:840-848).
+        static_assert(sizeof(DsrtSphere) == 24, "sphere layout");
+        std::vector<float4> rec((size_t)nspheres * 2);
+        std::vector<int> lights;
+        for (int i = 0; i < nspheres; ++i) {
+            const DsrtSphere& sp = spheres[i];
+            rec[2 * i] = make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius);
+            float mid;
+            memcpy(&mid, &sp.material_id, 4);
+            rec[2 * i + 1] = make_float4(1.0f / sp.radius, mid, 0.f, 0.f);       // IEEE division, as :501
+            const DsrtMaterial& m = mats[sp.material_id];
+            if (m.type == DSRT_MAT_DIFFUSE_LIGHT && (m.emissive.x > 0 || m.emissive.y > 0 || m.emissive.z > 0))
+                lights.push_back(i);
+        }
+        CK(cudaMalloc(&ctx->d_spheres, sizeof(float4) * rec.size()));
+        CK(cudaMemcpy(ctx->d_spheres, rec.data(), sizeof(float4) * rec.size(), cudaMemcpyHostToDevice));
+        ctx->nspheres = nspheres;
+        if (!lights.empty()) {
+            CK(cudaMalloc(&ctx->d_sphere_lights, sizeof(int) * lights.size()));
+            CK(cudaMemcpy(ctx->d_sphere_lights, lights.data(), sizeof(int) * lights.size(), cudaMemcpyHostToDevice));
+            ctx->nsphere_lights = (int)lights.size();
+        }
     }
     if (ntris > 0) {
         static_assert(sizeof(DsrtTriangle) == 116, "triangle layout");
@@ -300,8 +334,7 @@ extern "C" int dsrt_scene_upload(dsrt_ctx* ctx, const DsrtTriangle* tris, int nt
                                  const DsrtTextureHeader* textures, int ntextures,
                                  const float* texture_pool, int texture_pool_floats) {
     if (!ctx) return DSRT_EINVAL;
-    (void)spheres;
-    return scene_upload_impl(ctx, false, tris, ntris, mats, nmats, nspheres, textures, ntextures,
+    return scene_upload_impl(ctx, false, tris, ntris, mats, nmats, spheres, nspheres, textures, ntextures,
                              texture_pool, texture_pool_floats);
 }
 
@@ -310,7 +343,7 @@ extern "C" int dsrt_scene_upload_device(dsrt_ctx* ctx, const DsrtTriangle* tris_
                                         const DsrtTextureHeader* textures_device, int ntextures,
                                         const float* texture_pool_device, int texture_pool_floats) {
     if (!ctx) return DSRT_EINVAL;
-    return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, nspheres,
+    return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, nullptr, nspheres,
                              textures_device, ntextures, texture_pool_device, texture_pool_floats);
 }
 
@@ -368,6 +401,10 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
     }
     fc.num_textures = ctx->ntex;
     fc.texture_pool_floats = ctx->pool_floats;
+    fc.spheres = ctx->d_spheres;
+    fc.sphere_lights = ctx->d_sphere_lights;
+    fc.num_spheres = ctx->nspheres;
+    fc.num_sphere_lights = ctx->nsphere_lights;
 }
 
 void fill_camera(const DsrtCamera* cam, FrameConst& fc) {
@@ -612,7 +649,7 @@ extern "C" int dsrt_trace_closest_device(dsrt_ctx* ctx, const void* rays_device,
     if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
     if (n == 0) return DSRT_OK;
     CK(cudaSetDevice(ctx->device));
-    launch_trace_closest(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
+    launch_trace_closest(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes, SphereSet{ctx->d_spheres, ctx->nspheres},
                          (const float4*)rays_device, n, (float4*)hits_device,
                          ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());
@@ -624,7 +661,7 @@ extern "C" int dsrt_trace_occluded_device(dsrt_ctx* ctx, const void* rays_device
     if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "trace before dsrt_scene_upload");
     if (n == 0) return DSRT_OK;
     CK(cudaSetDevice(ctx->device));
-    launch_trace_occluded(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes,
+    launch_trace_occluded(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes, SphereSet{ctx->d_spheres, ctx->nspheres},
                           (const float4*)rays_device, n, (uint8_t*)occluded_device,
                           ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());

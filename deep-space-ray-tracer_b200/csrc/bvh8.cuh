@@ -223,7 +223,7 @@ struct LaneTrav {
     float idx, idy, idz;
     float tmin, tmax;             // tmax shrinks to the closest accepted hit
     float hu, hv;
-    int htri;                     // position in the leaf-ordered record array, -1 = none
+    int htri;                     // position in the leaf-ordered record array, -1 = none, -2 - i = sphere i
     uint32_t octinv;
     uint2 ngroup;
     uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
@@ -280,6 +280,42 @@ struct LaneTrav {
             ngroup = stack.pop();
         }
         return false;
+    }
+
+    // The brute-force sphere loop of the reference's scene_hit (gpu_render.cu:530-546), run once
+    // the triangles are done: the interval's upper end is the closest triangle hit and it is
+    // closed on both ends, so a sphere at exactly that distance replaces the triangle.
+    // hit_sphere (gpu_render.cu:478-504) as compiled: c = fma(-r, r, dot(oc, oc)),
+    // discriminant = fma(hb, hb, -rn(a * c)), IEEE sqrt and divisions.
+    // Records: 2 x float4 per sphere {centre.xyz, radius | 1/radius, bits(material), 0, 0}.
+    // A sphere hit is reported as htri = -2 - index.
+    // `a` = dot(dir, dir) is loop-invariant and the reference's compiler hoists and contracts it
+    // differently in its inlined copies: in render_kernel's closest-hit loop it is
+    // fma(z,z, fma(y,y, rn(x*x))) (cuobjdump: FMUL x,x; FFMA y,y; FFMA z,z), in the shadow-ray
+    // loop and in the stand-alone scene_hit the usual fma(z,z, fma(x,x, rn(y*y))).  On a
+    // sphere's silhouette and terminator that last bit decides hit or miss, so the render path
+    // passes x_first = true for its closest-hit rays.
+    __device__ __forceinline__ void spheres_pass(const float4* __restrict__ sph, int n, bool x_first) {
+        if (any_hit && htri != -1) return;
+        const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
+        const float a = (x_first && !any_hit) ? __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, __fmul_rn(dir.x, dir.x)))
+                                              : vdot(dir, dir);
+        for (int i = 0; i < n; ++i) {
+            const float4 s0 = __ldg(&sph[2 * i]);
+            const V3 oc = vsub(orig, v3(s0.x, s0.y, s0.z));
+            const float half_b = vdot(oc, dir);
+            const float c = __fmaf_rn(-s0.w, s0.w, vdot(oc, oc));
+            const float disc = __fmaf_rn(half_b, half_b, -__fmul_rn(a, c));
+            if (disc < 0.0f) continue;
+            const float sq = __fsqrt_rn(disc);
+            float root = __fdiv_rn(__fsub_rn(-half_b, sq), a);
+            if (root < tmin || root > tmax) {
+                root = __fdiv_rn(__fadd_rn(-half_b, sq), a);
+                if (root < tmin || root > tmax) continue;
+            }
+            tmax = root; hu = 0.0f; hv = 0.0f; htri = -2 - i;
+            if (any_hit) return;
+        }
     }
 };
 

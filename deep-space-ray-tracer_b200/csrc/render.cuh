@@ -33,7 +33,10 @@ struct FrameConst {
     const float4* materials;          // DsrtMaterial as 3 x float4
     const DsrtTextureHeader* textures;
     const float* texture_pool;
+    const float4* spheres;            // 2 x float4 per sphere: centre.xyz, radius | 1/radius, bits(material), 0, 0
+    const int* sphere_lights;         // indices of the emissive spheres, in sphere order (gpu_render.cu:842-848)
     int num_nodes, num_textures, texture_pool_floats;
+    int num_spheres, num_sphere_lights;
     float scene_lo[3], scene_hi[3];   // scene bounds padded by 2^-16 of the scene size (root-box test)
     // camera (reference GPUCamera fields that the kernel reads)
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
@@ -51,7 +54,8 @@ struct FrameConst {
     // work memory
     float4* rq_o[2];                  // ray queue: origin.xyz, bits(path)
     float4* rq_d[2];                  // ray queue: dir.xyz, unused
-    float4* hits;                     // t,u,v,bits(uploaded triangle index) per queue entry
+    float4* hits;                     // t,u,v,bits(id) per queue entry; id = uploaded triangle index,
+                                      // -1 = miss, -2 - i = sphere i
     float4* st_a;                     // per path: throughput.xyz, bits(rng state / draw index)
     float4* st_b;                     // per path: L.xyz (clamped when finished), bits(depth)
     float4* sq_o;                     // shadow queue: origin.xyz, bits(path | final<<31)
@@ -78,10 +82,11 @@ void launch_tonemap(const float* accum, unsigned char* rgb, int W, int H, float 
 void launch_lcg_seed(uint32_t* rng_pix, int W, int H, uint32_t seed32, cudaStream_t s);
 
 // Generic traversal over an array of rays {ox,oy,oz,tmin | dx,dy,dz,tmax}.
-void launch_trace_closest(const uint4* nodes, const float4* tri_records, int num_nodes,
+struct SphereSet { const float4* records; int count; };
+void launch_trace_closest(const uint4* nodes, const float4* tri_records, int num_nodes, SphereSet spheres,
                           const float4* rays, int n, float4* hits, uint32_t* fetch_counter,
                           int blocks, cudaStream_t s);
-void launch_trace_occluded(const uint4* nodes, const float4* tri_records, int num_nodes,
+void launch_trace_occluded(const uint4* nodes, const float4* tri_records, int num_nodes, SphereSet spheres,
                            const float4* rays, int n, uint8_t* occluded, uint32_t* fetch_counter,
                            int blocks, cudaStream_t s);
 void launch_camera_rays(const FrameConst& fc, float jx, float jy, float4* rays, cudaStream_t s);

@@ -33,7 +33,7 @@ extern "C" {
 #define DSRT_EINVAL       -1   /* bad argument */
 #define DSRT_ECUDA        -2   /* a CUDA runtime call failed */
 #define DSRT_ENOSCENE     -3   /* render/trace before dsrt_scene_upload */
-#define DSRT_EUNSUPPORTED -4   /* feature of GPUScene not built yet (spheres) */
+#define DSRT_EUNSUPPORTED -4   /* combination not supported (spheres through the device-pointer upload) */
 #define DSRT_EIO          -5   /* file could not be read/written */
 #define DSRT_ENOMEM       -6
 
@@ -54,8 +54,11 @@ void* dsrt_stream(dsrt_ctx* ctx);
  * Copies the reference-layout arrays to the device and builds, on the GPU, a Morton-sorted
  * LBVH that is collapsed by surface area into an 8-wide BVH with quantised child boxes
  * (80-byte nodes) and 48-byte triangle records in leaf order.  Done once per mesh, not per
- * frame.  Spheres are part of GPUScene but never instantiated by the reference's main();
- * nspheres > 0 returns DSRT_EUNSUPPORTED. */
+ * frame.  Spheres (never instantiated by the reference's main(), but part of GPUScene) are
+ * intersected by a brute-force loop after the triangles exactly as the reference's scene_hit
+ * does (gpu_render.cu:530-546); emissive ones switch the diffuse bounce to the reference's
+ * light/BRDF mixture sampling (gpu_render.cu:838-932).  The parity hooks report a sphere hit
+ * as tri = -2 - sphere index. */
 int dsrt_scene_upload(dsrt_ctx* ctx,
                       const DsrtTriangle* tris, int ntris,
                       const DsrtMaterial* mats, int nmats,
@@ -150,6 +153,30 @@ void dsrt_camera_look_at_origin(const float lookfrom[3], float vfov_deg, int wid
  * diffuse_only != 0 gives lambertian-only materials (BASELINE config 5). */
 int dsrt_synth_mesh(int ntris, uint32_t seed, int diffuse_only,
                     DsrtTriangle* tris, DsrtMaterial* mats, int max_mats);
+/* OBJ + MTL (+ map_Kd textures) -> the arrays dsrt_scene_upload takes.  Replaces the reference's
+ * scene ingestion: triangle_mesh (inc/triangle_mesh.h:75-255: OBJ/MTL parser, MTL -> material
+ * mapping, fan triangulation, flat normals) followed by the flattening half of build_gpu_scene
+ * (src/gpu_scene_builder.cpp:72-138, 199-282, 518-551: material table by first use, texture
+ * registry, sRGB -> linear float pool).  `scale` multiplies the vertex positions in double, as
+ * triangle_mesh's constructor argument does.  Returns DSRT_EIO when the OBJ cannot be opened
+ * (the reference silently continues with an empty mesh).  Texture files are decoded in-process
+ * (PNG, binary PNM, BMP, TGA); an undecodable file becomes a 1x1 white texture, the
+ * reference's own failure path. */
+typedef struct dsrt_mesh dsrt_mesh;
+typedef struct DsrtMeshView {
+    const DsrtTriangle*      triangles;      int32_t num_triangles;
+    const DsrtMaterial*      materials;      int32_t num_materials;
+    const DsrtTextureHeader* textures;       int32_t num_textures;
+    const float*             texture_pool;   int32_t texture_pool_floats;
+    int32_t num_vertices, num_uvs;           /* `v` and `vt` records read */
+    int32_t skipped_faces;                   /* triangles dropped for an out-of-range vertex index */
+    int32_t textures_failed;                 /* textures replaced by 1x1 white */
+    int32_t textures_flipped;                /* 1 = pool rows are bottom-up (inc/texture.h:133 side effect) */
+} DsrtMeshView;
+int  dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh** out);
+int  dsrt_mesh_view(const dsrt_mesh* mesh, DsrtMeshView* view);     /* pointers valid until dsrt_mesh_free */
+void dsrt_mesh_free(dsrt_mesh* mesh);
+
 /* Binary P6 exactly as gpu_render.cu:1100-1107 writes it; PNG (8-bit RGB, zlib) replaces
  * the ImageMagick subprocess of main.cpp:28-36. */
 int dsrt_write_ppm(const char* path, const unsigned char* rgb, int width, int height);

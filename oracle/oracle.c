@@ -86,6 +86,9 @@ typedef struct {           /* GPUBVHNode semantics, gpu_scene.h:77-85 */
     int left, right, tri_offset, tri_count;
 } OrNode;
 
+typedef struct { float center[3], radius; int material_id, pad; } OrSphere;      /* GPUSphere, gpu_scene.h:50-55 */
+typedef struct { int width, height, offset; } OrTexHeader;                       /* GPUTextureHeader, gpu_scene.h:28-32 */
+
 struct OrScene {
     int n, nmats;
     float* tris;           /* n x 29 */
@@ -94,6 +97,9 @@ struct OrScene {
     OrNode* nodes;
     int num_nodes, cap_nodes;
     int max_leaf;
+    OrSphere* spheres; int num_spheres;
+    OrTexHeader* textures; int num_textures;
+    float* texture_pool; int texture_pool_floats;
 };
 
 #define MAT_LAMBERTIAN 0
@@ -193,9 +199,26 @@ OrScene* or_scene_create(const float* tris, int n, const void* mats, int nmats) 
     return s;
 }
 
+/* GPUScene.spheres / .textures / .texture_pool (gpu_scene.h:116-173) */
+void or_scene_set_spheres(OrScene* s, const void* spheres, int n) {
+    free(s->spheres);
+    s->spheres = (OrSphere*)malloc(sizeof(OrSphere) * (size_t)(n > 0 ? n : 1));
+    memcpy(s->spheres, spheres, sizeof(OrSphere) * (size_t)n);
+    s->num_spheres = n;
+}
+void or_scene_set_textures(OrScene* s, const void* headers, int n, const float* pool, int pool_floats) {
+    free(s->textures); free(s->texture_pool);
+    s->textures = (OrTexHeader*)malloc(sizeof(OrTexHeader) * (size_t)(n > 0 ? n : 1));
+    memcpy(s->textures, headers, sizeof(OrTexHeader) * (size_t)n);
+    s->texture_pool = (float*)malloc(sizeof(float) * (size_t)(pool_floats > 0 ? pool_floats : 1));
+    memcpy(s->texture_pool, pool, sizeof(float) * (size_t)pool_floats);
+    s->num_textures = n; s->texture_pool_floats = pool_floats;
+}
+
 void or_scene_destroy(OrScene* s) {
     if (!s) return;
-    free(s->tris); free(s->mats); free(s->indices); free(s->nodes); free(s);
+    free(s->tris); free(s->mats); free(s->indices); free(s->nodes);
+    free(s->spheres); free(s->textures); free(s->texture_pool); free(s);
 }
 int or_scene_num_nodes(const OrScene* s) { return s->num_nodes; }
 int or_scene_max_leaf(const OrScene* s) { return s->max_leaf; }
@@ -205,6 +228,7 @@ typedef struct { f3 orig, dir; } Ray;
 
 typedef struct {
     float t; f3 p; f3 normal; int mat_id, tri_tex_id, tri_index; float u, v; int front_face;
+    int sphere_index;      /* not in the reference's HitRecord: which sphere, for the hooks (-1 = triangle) */
 } Hit;
 
 /* gpu_render.cu:285-315.  Note `t_max <= t_min`: a box of zero thickness is never hit. */
@@ -254,6 +278,7 @@ static int hit_triangle_index(const OrScene* s, int tri_index, const Ray* ray, f
     memcpy(&rec->mat_id, &T[27], 4);
     memcpy(&rec->tri_tex_id, &T[28], 4);
     rec->tri_index = tri_index;
+    rec->sphere_index = -1;
     return 1;
 }
 
@@ -313,11 +338,76 @@ static int bvh_hit_closest(const OrScene* s, const Ray* ray, float t_min, float 
     return hit_anything;
 }
 
-/* gpu_render.cu:509-551 with num_spheres == 0 (the product never creates spheres) */
-static int scene_hit(const OrScene* s, const Ray* ray, float t_min, float t_max, Hit* rec) {
+/* gpu_render.cu:478-504 as compiled for sm_100a (cuobjdump of hit_sphere):
+ * c = fma(-r, r, dot(oc, oc)), discriminant = fma(hb, hb, -rn(a * c)), IEEE sqrt and divisions,
+ * p = fma(dir, t, orig), normal = (p - centre) * (1 / r). */
+/* x_first: dot(dir, dir) as render_kernel's closest-hit loop has it after hoisting,
+ * fma(z,z, fma(y,y, rn(x*x))); elsewhere (shadow loop, stand-alone scene_hit) the usual f3_dot. */
+static int hit_sphere(const OrSphere* sph, const Ray* ray, float t_min, float t_max, int x_first, float* t_out, f3* normal_out) {
+    const f3 centre = F3(sph->center[0], sph->center[1], sph->center[2]);
+    const f3 oc = f3_sub(ray->orig, centre);
+    const f3 d = ray->dir;
+    const float a = x_first ? fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)) : f3_dot(d, d);
+    const float half_b = f3_dot(oc, ray->dir);
+    const float c = fmaf(-sph->radius, sph->radius, f3_dot(oc, oc));
+    const float disc = fmaf(half_b, half_b, -(a * c));
+    if (disc < 0.0f) return 0;
+    const float sqrtd = sqrtf(disc);
+    float root = (-half_b - sqrtd) / a;
+    if (root < t_min || root > t_max) {
+        root = (-half_b + sqrtd) / a;
+        if (root < t_min || root > t_max) return 0;
+    }
+    *t_out = root;
+    const f3 p = f3_madd(ray->dir, root, ray->orig);
+    *normal_out = f3_scale(f3_sub(p, centre), 1.0f / sph->radius);
+    return 1;
+}
+
+/* gpu_render.cu:509-551: BVH triangles, then the brute-force sphere loop on [t_min, closest] */
+static int scene_hit_ctx(const OrScene* s, const Ray* ray, float t_min, float t_max, int x_first, Hit* rec) {
+    Hit best;
+    memset(&best, 0, sizeof(best));
+    int hit_any = 0;
+    float closest = t_max;
     Hit tri_rec;
-    if (bvh_hit_closest(s, ray, t_min, t_max, &tri_rec)) { *rec = tri_rec; return 1; }
-    return 0;
+    memset(&tri_rec, 0, sizeof(tri_rec));
+    if (bvh_hit_closest(s, ray, t_min, closest, &tri_rec)) { hit_any = 1; closest = tri_rec.t; best = tri_rec; }
+    for (int i = 0; i < s->num_spheres; ++i) {
+        float t_hit; f3 n_hit;
+        if (hit_sphere(&s->spheres[i], ray, t_min, closest, x_first, &t_hit, &n_hit)) {
+            hit_any = 1;
+            closest = t_hit;
+            best.t = t_hit;
+            best.p = f3_madd(ray->dir, t_hit, ray->orig);
+            best.front_face = f3_dot(ray->dir, n_hit) < 0.0f;             /* set_face_normal, :275-278 */
+            best.normal = best.front_face ? n_hit : f3_neg(n_hit);
+            best.mat_id = s->spheres[i].material_id;
+            best.tri_tex_id = -1;
+            best.tri_index = -1;
+            best.sphere_index = i;
+            best.u = 0.0f; best.v = 0.0f;
+        }
+    }
+    if (hit_any) *rec = best;
+    return hit_any;
+}
+
+static int scene_hit(const OrScene* s, const Ray* ray, float t_min, float t_max, Hit* rec) {
+    return scene_hit_ctx(s, ray, t_min, t_max, 0, rec);
+}
+
+/* tex2D, gpu_render.cu:232-259: nearest texel, wrap by x - floor(x), white when out of range */
+static f3 tex2D(const OrScene* s, int tex_id, float u, float v) {
+    if (tex_id < 0 || tex_id >= s->num_textures || !s->textures || !s->texture_pool) return F3(1.f, 1.f, 1.f);
+    const OrTexHeader th = s->textures[tex_id];
+    u = u - floorf(u);
+    v = v - floorf(v);
+    const int i = (int)(u * (float)(th.width - 1));
+    const int j = (int)((1.0f - v) * (float)(th.height - 1));
+    const int idx = th.offset + (j * th.width + i) * 3;
+    if (idx < 0 || idx + 2 >= s->texture_pool_floats) return F3(1.f, 1.f, 1.f);
+    return F3(s->texture_pool[idx], s->texture_pool[idx + 1], s->texture_pool[idx + 2]);
 }
 
 /* ---- random numbers ----------------------------------------------------------------------- */
@@ -370,9 +460,50 @@ static f3 reflect_ref(f3 v, f3 n) {                           /* gpu_render.cu:1
     return F3(fmaf(-n.x, two_d, v.x), fmaf(-n.y, two_d, v.y), fmaf(-n.z, two_d, v.z));
 }
 
+/* sample_cosine_hemisphere + build_onb + random_cosine_direction, gpu_render.cu:99-141 */
+static f3 sample_cosine_hemisphere(f3 normal, Rng* rng, float* pdf_out) {
+    const f3 w = f3_norm(normal);
+    const f3 a = fabsf(w.x) > 0.9f ? F3(0.f, 1.f, 0.f) : F3(1.f, 0.f, 0.f);
+    const f3 vv = f3_norm(f3_cross(w, a));
+    const f3 uu = f3_cross(vv, w);
+    const float r1 = rand01(rng), r2 = rand01(rng);
+    const float lz = sqrtf(1.0f - r2);
+    const float phi = (PI_F + PI_F) * r1;
+    const float sr2 = sqrtf(r2);
+    const float lx = cosf(phi) * sr2, ly = sinf(phi) * sr2;
+    f3 wd = F3(fmaf(w.x, lz, fmaf(uu.x, lx, vv.x * ly)),
+               fmaf(w.y, lz, fmaf(uu.y, lx, vv.y * ly)),
+               fmaf(w.z, lz, fmaf(uu.z, lx, vv.z * ly)));
+    wd = f3_norm(wd);
+    const float cos_b = fmaxf(0.0f, f3_dot(wd, normal));
+    *pdf_out = cos_b > 0.0f ? cos_b / PI_F : 0.0f;
+    return wd;
+}
+
+/* sample_sphere_light_direction, gpu_render.cu:145-188 */
+static f3 sample_sphere_light_direction(const OrSphere* sph, f3 origin, Rng* rng, float* pdf_out) {
+    const float z = fmaf(2.0f, rand01(rng), -1.0f);
+    const float phi = (PI_F + PI_F) * rand01(rng);
+    const float r = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    const f3 local = F3(r * cosf(phi), r * sinf(phi), z);
+    const f3 centre = F3(sph->center[0], sph->center[1], sph->center[2]);
+    const f3 p_light = f3_madd(local, sph->radius, centre);
+    const f3 to_light = f3_sub(p_light, origin);
+    const float dist2 = f3_dot(to_light, to_light);
+    const float dist = sqrtf(dist2);
+    if (dist <= 0.0f) { *pdf_out = 0.0f; return F3(0.f, 0.f, 1.f); }
+    const f3 wi = f3_scale(to_light, 1.0f / dist);
+    const f3 n_light = f3_norm(f3_sub(p_light, centre));
+    const float cos_l = fmaxf(0.0f, f3_dot(n_light, f3_scale(wi, -1.0f)));
+    if (cos_l <= 0.0f) { *pdf_out = 0.0f; return wi; }
+    const float area = ((4.0f * PI_F) * sph->radius) * sph->radius;
+    *pdf_out = dist2 / (cos_l * area);
+    return wi;
+}
+
 typedef struct { uint64_t primary, bounce, shadow; } Counts;
 
-/* ray_color, gpu_render.cu:715-936 (no emissive spheres: the :838-927 branch is unreachable) */
+/* ray_color, gpu_render.cu:715-936 */
 static f3 ray_color(const OrScene* s, Ray ray, Rng* rng, int max_depth_param, int sun_enabled,
                     f3 sun_dir, f3 sun_rad, Counts* cnt) {
     f3 L = F3(0, 0, 0), T = F3(1, 1, 1);
@@ -386,13 +517,21 @@ static f3 ray_color(const OrScene* s, Ray ray, Rng* rng, int max_depth_param, in
         }
         Hit rec;
         if (depth == 0) cnt->primary++; else cnt->bounce++;
-        if (!scene_hit(s, &ray, 0.001f, 1e9f, &rec)) break;
+        if (!scene_hit_ctx(s, &ray, 0.001f, 1e9f, 1, &rec)) break;      /* render_kernel's closest-hit context */
         const OrMaterial* mat = &s->mats[rec.mat_id];
         if (mat->type == MAT_DIFFUSE_LIGHT) {
             L = F3(fmaf(T.x, mat->emissive[0], L.x), fmaf(T.y, mat->emissive[1], L.y), fmaf(T.z, mat->emissive[2], L.z));
             break;
         }
-        const f3 albedo = F3(mat->albedo[0], mat->albedo[1], mat->albedo[2]);   /* textures: not in the oracle */
+        f3 albedo = F3(mat->albedo[0], mat->albedo[1], mat->albedo[2]);
+        if (rec.tri_tex_id >= 0) {                             /* gpu_render.cu:765-774 */
+            const float* T9 = tri_ptr(s, rec.tri_index);
+            const float w = 1.0f - rec.u - rec.v;
+            /* w*uv0 + u*uv1 + v*uv2 as compiled: fma(v,uv2, fma(w,uv0, rn(u*uv1))) */
+            const float u_tex = fmaf(rec.v, T9[24], fmaf(w, T9[18], rec.u * T9[21]));
+            const float v_tex = fmaf(rec.v, T9[25], fmaf(w, T9[19], rec.u * T9[22]));
+            albedo = f3_mul(albedo, tex2D(s, rec.tri_tex_id, u_tex, v_tex));
+        }
         if (mat->type == MAT_DIELECTRIC) {                     /* gpu_render.cu:621-661 */
             float eta = mat->ref_idx;
             if (eta <= 0.0f || !isfinite(eta)) eta = 1.5f;
@@ -445,25 +584,54 @@ static f3 ray_color(const OrScene* s, Ray ray, Rng* rng, int max_depth_param, in
                 }
             }
         }
-        {                                                      /* gpu_render.cu:99-141, 852-866 */
-            const f3 w = f3_norm(rec.normal);
-            const f3 a = fabsf(w.x) > 0.9f ? F3(0.f, 1.f, 0.f) : F3(1.f, 0.f, 0.f);
-            const f3 vv = f3_norm(f3_cross(w, a));
-            const f3 uu = f3_cross(vv, w);
-            const float r1 = rand01(rng), r2 = rand01(rng);
-            const float lz = sqrtf(1.0f - r2);
-            const float phi = (PI_F + PI_F) * r1;
-            const float sr2 = sqrtf(r2);
-            const float lx = cosf(phi) * sr2, ly = sinf(phi) * sr2;
-            f3 wd = F3(fmaf(w.x, lz, fmaf(uu.x, lx, vv.x * ly)),
-                       fmaf(w.y, lz, fmaf(uu.y, lx, vv.y * ly)),
-                       fmaf(w.z, lz, fmaf(uu.z, lx, vv.z * ly)));
-            wd = f3_norm(wd);
-            const float cos_b = fmaxf(0.0f, f3_dot(wd, rec.normal));
-            const float pdf_b = cos_b > 0.0f ? cos_b / PI_F : 0.0f;
+        /* gpu_render.cu:838-850: emissive spheres are re-counted at every diffuse hit */
+        int num_lights = 0;
+        for (int i = 0; i < s->num_spheres; ++i) {
+            const OrMaterial* lm = &s->mats[s->spheres[i].material_id];
+            if (lm->type == MAT_DIFFUSE_LIGHT && (lm->emissive[0] > 0 || lm->emissive[1] > 0 || lm->emissive[2] > 0)) num_lights++;
+        }
+        if (num_lights == 0) {                                 /* gpu_render.cu:852-866 */
+            float pdf_b;
+            const f3 wd = sample_cosine_hemisphere(rec.normal, rng, &pdf_b);
             if (pdf_b <= 0.0f) break;
-            T = f3_mul(T, f3_scale(albedo, pdf_b / pdf_b));
+            const float cos_b = fmaxf(0.0f, f3_dot(wd, rec.normal));
+            T = f3_mul(T, f3_scale(albedo, (cos_b / PI_F) / pdf_b));
             ray.orig = rec.p; ray.dir = wd;
+            continue;
+        }
+        {                                                      /* gpu_render.cu:868-932 */
+            f3 dir;
+            float pdf_val = 0.0f;
+            const float choose = rand01(rng);
+            if (choose < 0.5f) {
+                int k = (int)(rand01(rng) * (float)num_lights);
+                if (k >= num_lights) k = num_lights - 1;
+                int found = 0, light_idx = -1;
+                for (int i = 0; i < s->num_spheres; ++i) {
+                    const OrMaterial* lm = &s->mats[s->spheres[i].material_id];
+                    if (lm->type == MAT_DIFFUSE_LIGHT && (lm->emissive[0] > 0 || lm->emissive[1] > 0 || lm->emissive[2] > 0)) {
+                        if (found == k) { light_idx = i; break; }
+                        found++;
+                    }
+                }
+                float pdf_cond = 0.0f;
+                dir = sample_sphere_light_direction(&s->spheres[light_idx], rec.p, rng, &pdf_cond);
+                if (pdf_cond <= 0.0f) break;
+                const float cos_s = fmaxf(0.0f, f3_dot(dir, rec.normal));
+                if (cos_s <= 0.0f) break;
+                const float pdf_light = pdf_cond / (float)num_lights;
+                const float pdf_brdf = cos_s / PI_F;
+                pdf_val = fmaf(0.5f, pdf_light, 0.5f * pdf_brdf);
+            } else {
+                float pdf_b = 0.0f;
+                dir = sample_cosine_hemisphere(rec.normal, rng, &pdf_b);
+                if (pdf_b <= 0.0f) break;
+                pdf_val = 0.5f * pdf_b;
+            }
+            const float cos_s = fmaxf(0.0f, f3_dot(dir, rec.normal));
+            const float wgt = (cos_s / PI_F) / pdf_val;
+            T = f3_mul(T, f3_scale(albedo, wgt));
+            ray.orig = rec.p; ray.dir = dir;
         }
     }
     return F3(clamp01(L.x), clamp01(L.y), clamp01(L.z));
@@ -493,7 +661,7 @@ static void first_hit_row(int y, void* arg) {
         Hit rec;
         int hit = scene_hit(J->s, &r, 0.001f, 1e9f, &rec);
         int i = x + y * J->W;
-        J->tri[i] = hit ? rec.tri_index : -1;
+        J->tri[i] = hit ? (rec.sphere_index >= 0 ? -2 - rec.sphere_index : rec.tri_index) : -1;
         J->t[i] = hit ? rec.t : 1e9f;
         J->u[i] = hit ? rec.u : 0.f;
         J->v[i] = hit ? rec.v : 0.f;
@@ -523,7 +691,7 @@ static void trace_chunk(int c, void* arg) {
         Hit rec;
         int hit = scene_hit(J->s, &r, q[3], q[7], &rec);
         if (J->occ) { J->occ[i] = (uint8_t)hit; continue; }
-        J->tri[i] = hit ? rec.tri_index : -1;
+        J->tri[i] = hit ? (rec.sphere_index >= 0 ? -2 - rec.sphere_index : rec.tri_index) : -1;
         J->t[i] = hit ? rec.t : q[7];
         J->u[i] = hit ? rec.u : 0.f;
         J->v[i] = hit ? rec.v : 0.f;

@@ -27,6 +27,12 @@ typedef struct OrScene OrScene;
  * bytes in the GPUMaterial layout (gpu_scene.h:34-45).  Builds the reference's median-split
  * binary BVH (gpu_scene_builder.cpp:343-459). */
 OrScene* or_scene_create(const float* tris, int n, const void* mats, int nmats);
+/* spheres: n x 24 bytes in the GPUSphere layout (gpu_scene.h:50-55); textures: n x 12-byte
+ * GPUTextureHeader + the float RGB pool they index (gpu_scene.h:28-32).  With spheres the
+ * hooks below report a sphere hit as tri = -2 - sphere index (the reference's HitRecord holds
+ * tri_index = -1 for them). */
+void     or_scene_set_spheres(OrScene* s, const void* spheres, int n);
+void     or_scene_set_textures(OrScene* s, const void* headers, int n, const float* pool, int pool_floats);
 void     or_scene_destroy(OrScene* s);
 int      or_scene_num_nodes(const OrScene* s);
 int      or_scene_max_leaf(const OrScene* s);

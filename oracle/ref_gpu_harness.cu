@@ -16,6 +16,8 @@
 #include "gpu_scene_builder.h"
 #include "hittable_list.h"
 #include "triangle.h"
+#include "triangle_mesh.h"
+#include "sphere.h"
 #include "material.h"
 #include "camera.h"
 
@@ -70,11 +72,44 @@ __global__ void ref_trace_kernel(const GPUScene* dscene, const float* rays, int 
 
 extern "C" {
 
+static camera make_ref_camera(const float lookfrom[3], float vfov, int W, int H, int spp, int max_depth) {
+    camera cam;
+    cam.image_width = W; cam.image_height = H;
+    cam.samples_per_pixel = spp; cam.max_depth = max_depth;
+    cam.vfov = vfov; cam.aperture = 0.0f;
+    cam.lookfrom = vec3(lookfrom[0], lookfrom[1], lookfrom[2]);
+    cam.lookat = vec3(0, 0, 0);
+    cam.vup = vec3(0, 1, 0);
+    cam.focus_dist = (cam.lookfrom - cam.lookat).length();
+    cam.initialize();
+    return cam;
+}
+
+static RefScene* finish_ref_scene(RefScene* R, const hittable_list& world, const camera& cam, const float sun_dir[3], int W, int H) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    R->scene = build_gpu_scene(world, cam, vec3(sun_dir[0], sun_dir[1], sun_dir[2]));
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&R->build_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    R->W = W; R->H = H;
+    if (cudaMalloc(&R->d_scene, sizeof(GPUScene)) != cudaSuccess ||
+        cudaMemcpy(R->d_scene, &R->scene, sizeof(GPUScene), cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete R;
+        return nullptr;
+    }
+    return R;
+}
+
 // tris: n x 29 floats in the reference's GPUTriangle layout (only v0,v1,v2 and material_id are
 // consumed; the reference recomputes its flat normals, which are compared with the ones given).
-void* ref_scene_create(const float* tris, int n, const RefMaterial* mats, int nmats,
-                       const float lookfrom[3], float vfov, int W, int H, int spp, int max_depth,
-                       const float sun_dir[3]) {
+// spheres: nspheres x {cx,cy,cz,radius,bits(material_id),pad} become reference `sphere` objects.
+void* ref_scene_create_ex(const float* tris, int n, const RefMaterial* mats, int nmats,
+                          const float* spheres, int nspheres,
+                          const float lookfrom[3], float vfov, int W, int H, int spp, int max_depth,
+                          const float sun_dir[3]) {
     std::vector<std::shared_ptr<material>> M;
     for (int i = 0; i < nmats; ++i) {
         const RefMaterial& m = mats[i];
@@ -96,31 +131,51 @@ void* ref_scene_create(const float* tris, int n, const RefMaterial* mats, int nm
         if (std::memcmp(nn, p + 9, 12) != 0) R->normal_mismatches++;
         world.add(t);
     }
-    camera cam;
-    cam.image_width = W; cam.image_height = H;
-    cam.samples_per_pixel = spp; cam.max_depth = max_depth;
-    cam.vfov = vfov; cam.aperture = 0.0f;
-    cam.lookfrom = vec3(lookfrom[0], lookfrom[1], lookfrom[2]);
-    cam.lookat = vec3(0, 0, 0);
-    cam.vup = vec3(0, 1, 0);
-    cam.focus_dist = (cam.lookfrom - cam.lookat).length();
-    cam.initialize();
-
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0);
-    R->scene = build_gpu_scene(world, cam, vec3(sun_dir[0], sun_dir[1], sun_dir[2]));
-    cudaEventRecord(e1);
-    cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&R->build_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    R->W = W; R->H = H;
-    if (cudaMalloc(&R->d_scene, sizeof(GPUScene)) != cudaSuccess ||
-        cudaMemcpy(R->d_scene, &R->scene, sizeof(GPUScene), cudaMemcpyHostToDevice) != cudaSuccess) {
-        delete R;
-        return nullptr;
+    for (int i = 0; i < nspheres; ++i) {
+        const float* p = spheres + (size_t)i * 6;
+        int mid;
+        std::memcpy(&mid, p + 4, 4);
+        world.add(std::make_shared<sphere>(vec3(p[0], p[1], p[2]), (double)p[3], M[(size_t)mid]));
     }
-    return R;
+    camera cam = make_ref_camera(lookfrom, vfov, W, H, spp, max_depth);
+    return finish_ref_scene(R, world, cam, sun_dir, W, H);
+}
+
+void* ref_scene_create(const float* tris, int n, const RefMaterial* mats, int nmats,
+                       const float lookfrom[3], float vfov, int W, int H, int spp, int max_depth,
+                       const float sun_dir[3]) {
+    return ref_scene_create_ex(tris, n, mats, nmats, nullptr, 0, lookfrom, vfov, W, H, spp, max_depth, sun_dir);
+}
+
+// The reference's own OBJ path: triangle_mesh (inc/triangle_mesh.h) with main.cpp's fallback
+// material, flattened by build_gpu_scene (materials, per-triangle textures through stb_image).
+void* ref_scene_create_obj(const char* obj_path, double scale,
+                           const float lookfrom[3], float vfov, int W, int H, int spp, int max_depth,
+                           const float sun_dir[3]) {
+    RefScene* R = new RefScene();
+    auto fallbackM = std::make_shared<lambertian>(vec3(0.73, 0.73, 0.73));      // main.cpp:241
+    auto mesh = std::make_shared<triangle_mesh>(std::string(obj_path), fallbackM, scale);
+    hittable_list world;
+    world.add(mesh);
+    camera cam = make_ref_camera(lookfrom, vfov, W, H, spp, max_depth);
+    return finish_ref_scene(R, world, cam, sun_dir, W, H);
+}
+
+// Copies the flattened scene arrays back from the device (what build_gpu_scene uploaded):
+// any pointer may be NULL; counts are returned through n[6] = {triangles, materials, spheres,
+// textures, texture_pool_floats, bvh_nodes}.
+int ref_scene_arrays(void* h, int n[6], void* tris, void* mats, void* spheres, void* tex_headers, float* pool) {
+    RefScene* R = (RefScene*)h;
+    if (!R) return -1;
+    const GPUScene& S = R->scene;
+    n[0] = S.num_triangles; n[1] = S.num_materials; n[2] = S.num_spheres; n[3] = S.num_textures;
+    n[4] = S.texture_pool_floats; n[5] = S.num_bvh_nodes;
+    if (tris && S.num_triangles) cudaMemcpy(tris, S.triangles, sizeof(GPUTriangle) * (size_t)S.num_triangles, cudaMemcpyDeviceToHost);
+    if (mats && S.num_materials) cudaMemcpy(mats, S.materials, sizeof(GPUMaterial) * (size_t)S.num_materials, cudaMemcpyDeviceToHost);
+    if (spheres && S.num_spheres) cudaMemcpy(spheres, S.spheres, sizeof(GPUSphere) * (size_t)S.num_spheres, cudaMemcpyDeviceToHost);
+    if (tex_headers && S.num_textures) cudaMemcpy(tex_headers, S.textures, sizeof(GPUTextureHeader) * (size_t)S.num_textures, cudaMemcpyDeviceToHost);
+    if (pool && S.texture_pool_floats) cudaMemcpy(pool, S.texture_pool, sizeof(float) * (size_t)S.texture_pool_floats, cudaMemcpyDeviceToHost);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int ref_scene_info(void* h, int* num_bvh_nodes, int* normal_mismatches, float* build_ms, float camera12[12]) {

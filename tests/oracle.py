@@ -25,6 +25,10 @@ def lib():
         L.or_scene_create.argtypes = [vp, i, vp, i]
         L.or_scene_destroy.argtypes = [vp]
         L.or_scene_destroy.restype = None
+        L.or_scene_set_spheres.argtypes = [vp, vp, i]
+        L.or_scene_set_spheres.restype = None
+        L.or_scene_set_textures.argtypes = [vp, vp, i, vp, i]
+        L.or_scene_set_textures.restype = None
         L.or_scene_num_nodes.argtypes = [vp]
         L.or_scene_max_leaf.argtypes = [vp]
         L.or_first_hits.argtypes = [vp, vp, i, i, f, f, vp, vp, vp, vp]
@@ -84,12 +88,21 @@ def philox(ctr, key):
 
 
 class Scene:
-    def __init__(self, tris, mats):
+    def __init__(self, tris, mats, spheres=None, textures=None, texture_pool=None):
         t = np.ascontiguousarray(tris)
         m = np.ascontiguousarray(mats)
         assert t.dtype.itemsize == 116 and m.dtype.itemsize == 48
         self._keep = (t, m)
         self.h = lib().or_scene_create(t.ctypes.data, len(t), m.ctypes.data, len(m))
+        if spheres is not None and len(spheres):
+            sp = np.ascontiguousarray(spheres)
+            assert sp.dtype.itemsize == 24
+            lib().or_scene_set_spheres(self.h, sp.ctypes.data, len(sp))
+        if textures is not None and len(textures):
+            th = np.ascontiguousarray(textures)
+            tp = np.ascontiguousarray(texture_pool, np.float32)
+            assert th.dtype.itemsize == 12
+            lib().or_scene_set_textures(self.h, th.ctypes.data, len(th), tp.ctypes.data, len(tp))
         self.num_nodes = lib().or_scene_num_nodes(self.h)
         self.max_leaf = lib().or_scene_max_leaf(self.h)
 

@@ -25,6 +25,11 @@ def lib():
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         _lib.ref_scene_create.restype = vp
         _lib.ref_scene_create.argtypes = [vp, i, vp, i, vp, f, i, i, i, i, vp]
+        _lib.ref_scene_create_ex.restype = vp
+        _lib.ref_scene_create_ex.argtypes = [vp, i, vp, i, vp, i, vp, f, i, i, i, i, vp]
+        _lib.ref_scene_create_obj.restype = vp
+        _lib.ref_scene_create_obj.argtypes = [C.c_char_p, C.c_double, vp, f, i, i, i, i, vp]
+        _lib.ref_scene_arrays.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         _lib.ref_scene_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(f), vp]
         _lib.ref_scene_set_seed.argtypes = [vp, C.c_ulonglong]
         _lib.ref_render.argtypes = [vp, vp, C.POINTER(f)]
@@ -38,15 +43,23 @@ def lib():
 class RefScene:
     """The reference's own build_gpu_scene + render_kernel on the same triangles."""
 
-    def __init__(self, tris, mats, lookfrom, sun_dir, width, height, spp, max_depth, vfov=40.0):
+    def __init__(self, tris, mats, lookfrom, sun_dir, width, height, spp, max_depth, vfov=40.0, spheres=None, obj=None, obj_scale=1.0):
+        """Triangles/materials (+ optional spheres, 24-byte GPUSphere records) become reference
+        scene-graph objects; or, with obj=<path>, the reference's own triangle_mesh loads the OBJ."""
         L = lib()
-        t = np.ascontiguousarray(tris)
-        m = np.ascontiguousarray(mats)
         lf = np.ascontiguousarray(lookfrom, dtype=np.float32)
         sd = np.ascontiguousarray(sun_dir, dtype=np.float32)
         self.W, self.H = width, height
-        self.h = L.ref_scene_create(t.ctypes.data, len(t), m.ctypes.data, len(m), lf.ctypes.data, vfov,
-                                    width, height, spp, max_depth, sd.ctypes.data)
+        if obj is not None:
+            self.h = L.ref_scene_create_obj(str(obj).encode(), float(obj_scale), lf.ctypes.data, vfov,
+                                            width, height, spp, max_depth, sd.ctypes.data)
+        else:
+            t = np.ascontiguousarray(tris)
+            m = np.ascontiguousarray(mats)
+            sp = np.ascontiguousarray(spheres) if spheres is not None and len(spheres) else None
+            self.h = L.ref_scene_create_ex(t.ctypes.data if len(t) else None, len(t), m.ctypes.data, len(m),
+                                           sp.ctypes.data if sp is not None else None, len(sp) if sp is not None else 0,
+                                           lf.ctypes.data, vfov, width, height, spp, max_depth, sd.ctypes.data)
         if not self.h:
             raise RuntimeError("ref_scene_create failed")
         nb, nm, ms = C.c_int(), C.c_int(), C.c_float()
@@ -54,6 +67,19 @@ class RefScene:
         L.ref_scene_info(self.h, C.byref(nb), C.byref(nm), C.byref(ms), cam.ctypes.data)
         self.num_bvh_nodes, self.normal_mismatches, self.build_ms = nb.value, nm.value, ms.value
         self.camera12 = cam
+
+    def arrays(self):
+        """The flattened arrays build_gpu_scene uploaded: dict of uint32/int32 word views."""
+        n = np.zeros(6, np.int32)
+        assert lib().ref_scene_arrays(self.h, n.ctypes.data, None, None, None, None, None) == 0
+        tris = np.zeros((n[0], 29), np.uint32)
+        mats = np.zeros((n[1], 12), np.uint32)
+        sph = np.zeros((n[2], 6), np.uint32)
+        th = np.zeros((n[3], 3), np.int32)
+        pool = np.zeros(n[4], np.uint32)
+        assert lib().ref_scene_arrays(self.h, n.ctypes.data, tris.ctypes.data, mats.ctypes.data, sph.ctypes.data,
+                                      th.ctypes.data, pool.ctypes.data) == 0
+        return {"counts": n, "tris": tris, "mats": mats, "spheres": sph, "textures": th, "pool": pool}
 
     def set_seed(self, seed: int):
         assert lib().ref_scene_set_seed(self.h, seed) == 0
