@@ -109,7 +109,7 @@ class ClockSampler:
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dsrt", choices=["dsrt", "reference"])
     ap.add_argument("--mode", default="frame", choices=["frame", "sample"])
@@ -123,7 +123,16 @@ def parse_args():
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--cpu_step", type=int, default=8, help="pixel stride of the CPU sample")
     ap.add_argument("--spb", type=int, default=0, help="samples of a pixel in flight together (0 = library default)")
-    return ap.parse_args()
+    ap.add_argument("--config", default="", choices=["", "c2", "c4", "c5"],
+                    help="BASELINE.json presets: c2 = the default; c4 = 3840x2160, 1000 spp (use with --mode sample); "
+                         "c5 = 10M triangles, diffuse only, depth 16, 1080p, 256 spp")
+    ap.add_argument("--no_ref_gpu", action="store_true", help="skip timing the reference's own GPU kernel beside the result")
+    a = ap.parse_args()
+    if a.config == "c4":
+        a.width, a.height, a.spp = 3840, 2160, 1000
+    elif a.config == "c5":
+        a.tris, a.diffuse_only, a.depth, a.spp = 10_000_000, True, 16, 256
+    return a
 
 
 def workload_name(a):
@@ -301,10 +310,14 @@ def run_dsrt(a, rank, world, local_rank):
         bpr = algorithmic_bytes_per_ray(a.tris)
         achieved = (ext_rays / world) * bpr / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         traffic = None
-        prof = ROOT / "profiles" / "extend_ncu_summary.json"
+        # DRAM bytes of the traversal launches of one step, from the committed `ncu --set full`
+        # capture of this same workload (profiles/trace_ncu_summary.json); null for other workloads
+        prof = ROOT / "profiles" / "trace_ncu_summary.json"
         if prof.exists():
             try:
-                traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+                pj = json.loads(prof.read_text())
+                if pj.get("workload") == workload_name(a):
+                    traffic = pj.get("dram_bytes_per_step")
             except Exception:  # noqa: BLE001
                 traffic = None
         out = {
@@ -330,10 +343,36 @@ def run_dsrt(a, rank, world, local_rank):
         }
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, tris, mats, poses)
+        if world == 1 and not a.no_ref_gpu and a.tris <= 2_000_000:
+            ctx.close()
+            out["ref_gpu_kernel"] = ref_gpu_kernel(a, tris, mats, poses, rays / a.steps)
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ref_gpu_kernel(a, tris, mats, poses, rays_per_frame):
+    """The reference's own CUDA path on the same B200 and frame (its CPU BVH build + its
+    megakernel, oracle/_ref/libref_gpu.so): reported beside the result, not part of it.  The
+    reference does not count rays; Mrays/s uses this path's ray count for the same frame."""
+    try:
+        import dsrt_b200 as d
+        import refgpu
+        if not refgpu.available():
+            return {"value": None, "note": "oracle/_ref/libref_gpu.so not present"}
+        cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+        ref = refgpu.RefScene(tris, mats, cam_pos, sun, a.width, a.height, a.spp, a.depth)
+        ms = [ref.render()[1] for _ in range(3)]
+        build_ms = ref.build_ms
+        ref.close()
+        best = min(ms[1:])
+        return {"value": rays_per_frame / (best * 1e3), "unit": "Mrays/s", "kernel_ms_per_frame": best,
+                "scene_build_ms_per_frame": build_ms,
+                "note": "render_kernel of the unmodified reference (one thread per pixel, LCG), second and third of 3 frames; "
+                        "its build_gpu_scene (CPU BVH + uploads, redone for every frame by its main()) is timed separately"}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "note": repr(e)}
 
 
 def cpu_baseline(a, tris, mats, poses):

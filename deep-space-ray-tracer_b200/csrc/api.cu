@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -66,6 +67,7 @@ struct dsrt_ctx {
     DsrtFrameStats fstats{};
     int stage_timing = 0;
     int spb_override = 0;
+    int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
     cudaEvent_t ev_frame[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
 
@@ -204,6 +206,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
         return DSRT_ECUDA;
     }
     launch_dims(&ctx->dims, device);
+    if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);      // tuning experiments only
     *out = ctx;
     return DSRT_OK;
 }
@@ -531,8 +534,13 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
             launch_trace(fc, cur ^ 1, depth & 1, ctx->dims, ctx->stream);
             launches += 3;
             cur ^= 1;
-            // Long depth limits (the reference default is 50): stop once nothing is in flight.
-            if (depth >= 7 && (depth & 3) == 3 && depth + 1 < fc.max_depth) {
+            // Few rays left: one thread per path finishes them in a single launch (render.cu: k_tail).
+            if (depth >= 1 && depth + 1 < fc.max_depth && ctx->tail_threshold > 0) {
+                launch_tail(fc, cur, depth + 1, (uint32_t)ctx->tail_threshold, ctx->stream);
+                ++launches;
+            }
+            // Stop enqueueing once nothing is in flight (checked every fourth bounce: one host sync).
+            if ((depth & 3) == 3 && depth + 1 < fc.max_depth) {
                 CK(cudaMemcpyAsync(ctx->h_pinned, ctx->counters, sizeof(uint32_t) * C_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 if (ctx->h_pinned[C_NIN] == 0u) break;      // shadow rays of this bounce were traced above

@@ -295,7 +295,10 @@ struct LaneTrav {
     // loop and in the stand-alone scene_hit the usual fma(z,z, fma(x,x, rn(y*y))).  On a
     // sphere's silhouette and terminator that last bit decides hit or miss, so the render path
     // passes x_first = true for its closest-hit rays.
-    __device__ __forceinline__ void spheres_pass(const float4* __restrict__ sph, int n, bool x_first) {
+#ifndef DSRT_SPHERES_INLINE
+#define DSRT_SPHERES_INLINE __forceinline__
+#endif
+    __device__ DSRT_SPHERES_INLINE void spheres_pass(const float4* __restrict__ sph, int n, bool x_first) {
         if (any_hit && htri != -1) return;
         const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
         const float a = (x_first && !any_hit) ? __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, __fmul_rn(dir.x, dir.x)))

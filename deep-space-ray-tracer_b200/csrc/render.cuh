@@ -16,6 +16,7 @@ enum {
     C_NSHADOW0 = 2,   // shadow rays pushed by k_shade at even depth
     C_NSHADOW1 = 3,   // ... at odd depth (double buffered, see k_advance)
     C_FETCH = 4,      // dynamic work counter of the traversal kernels
+    C_TAIL_DONE = 5,  // blocks of k_tail that have finished (reset by the last one)
     C_ZERO = 7,       // always 0 (an opaque zero for the traversal kernels, see trace_loop)
     C_COUNT = 8
 };
@@ -77,6 +78,9 @@ void launch_primary(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_trace(const FrameConst& fc, int cur, int shadow_slot, const LaunchDims& d, cudaStream_t s);
 void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
 void launch_advance(const FrameConst& fc, int depth, cudaStream_t s);
+// All remaining bounces of the rays in queue `cur` (traced, not yet shaded at depth0) in one launch --
+// a no-op unless at most `threshold` rays are left.
+void launch_tail(const FrameConst& fc, int cur, int depth0, uint32_t threshold, cudaStream_t s);
 void launch_resolve(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_tonemap(const float* accum, unsigned char* rgb, int W, int H, float inv_spp, float inv_gamma, cudaStream_t s);
 void launch_lcg_seed(uint32_t* rng_pix, int W, int H, uint32_t seed32, cudaStream_t s);

@@ -9,13 +9,25 @@
 // the node (frame-parallel, no collective) or one frame's samples are sharded across them
 // and summed with a single NCCL reduce.
 //
+// The mesh: the reference hard-codes ../../iss_model/ISS_stationary.obj (main.cpp:239) and
+// silently renders an empty scene when it is missing; here --obj <path> (default: that same
+// path) is loaded by dsrt_mesh_load_obj (OBJ + MTL + map_Kd textures, host/obj_loader.cpp), and
+// when the file cannot be opened the deterministic synthetic station stands in (the NASA model
+// is not redistributable with either tree).
+//
+// Frames are written by a writer thread per GPU (PPM, then the in-process PNG encoder that
+// replaces the reference's `magick` subprocess, main.cpp:28-36), so a GPU renders frame k+1
+// while frame k is being compressed.
+//
 // Extra, optional flags (defaults reproduce the reference): --width --height --spp
-// --max_depth --seed --synthetic_tris N --diffuse_only --gpus G --shard frame|sample
-// --frames a:b --rng philox|lcg --no_png --stats_json <file>.
+// --max_depth --seed --obj <path> --obj_scale S --synthetic_tris N --diffuse_only --gpus G
+// --shard frame|sample --frames a:b --rng philox|lcg --no_png --stats_json <file>.
 #include "dsrt.h"
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +50,8 @@ namespace {
 
 struct Options {
     std::string pose_file, out_dir = "output", stats_json, shard = "frame", rng = "philox";
+    std::string obj_path = "../../iss_model/ISS_stationary.obj";      // main.cpp:239
+    double obj_scale = 1.0;
     bool upscale = false, png = true, diffuse_only = false;
     int width = 800, height = 450, spp = 1000, max_depth = 50;
     int synthetic_tris = 1000000, gpus = 1, frame_begin = 0, frame_end = -1;
@@ -58,6 +72,8 @@ void parse_args(int argc, char** argv, Options& o) {
         else if (const char* v = next("--max_depth")) o.max_depth = std::atoi(v);
         else if (const char* v = next("--seed")) o.seed = std::strtoull(v, nullptr, 10);
         else if (const char* v = next("--synthetic_tris")) o.synthetic_tris = std::atoi(v);
+        else if (const char* v = next("--obj")) o.obj_path = v;
+        else if (const char* v = next("--obj_scale")) o.obj_scale = std::atof(v);
         else if (a == "--diffuse_only") o.diffuse_only = true;
         else if (const char* v = next("--gpus")) o.gpus = std::atoi(v);
         else if (const char* v = next("--shard")) o.shard = v;
@@ -79,6 +95,20 @@ void prepare_output_dir(const std::string& dir) {
     } else {
         fs::create_directories(dir);
     }
+}
+
+// Host copy of the scene in the layouts dsrt_scene_upload takes.
+struct SceneData {
+    std::vector<DsrtTriangle> tris;
+    std::vector<DsrtMaterial> mats;
+    std::vector<DsrtTextureHeader> tex;
+    std::vector<float> pool;
+};
+
+int upload(dsrt_ctx* ctx, const SceneData& sc) {
+    return dsrt_scene_upload(ctx, sc.tris.data(), (int)sc.tris.size(), sc.mats.data(), (int)sc.mats.size(), nullptr, 0,
+                             sc.tex.empty() ? nullptr : sc.tex.data(), (int)sc.tex.size(),
+                             sc.pool.empty() ? nullptr : sc.pool.data(), (int)sc.pool.size());
 }
 
 struct FrameJob {
@@ -119,9 +149,54 @@ bool save_frame(const Options& o, size_t index, const std::vector<unsigned char>
 
 std::mutex g_print;
 
+// Writes finished frames on its own thread so the GPU that produced them keeps rendering.
+// At most two frames are queued (the producer blocks beyond that).
+class FrameWriter {
+public:
+    FrameWriter(const Options& o, std::vector<FrameResult>& results) : o_(o), results_(results), th_([this] { run(); }) {}
+    ~FrameWriter() { finish(); }
+    void push(size_t slot, size_t index, std::vector<unsigned char>&& rgb) {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [this] { return q_.size() < 2; });
+        q_.push_back(Item{slot, index, std::move(rgb)});
+        cv_.notify_all();
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            if (closed_) return;
+            closed_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+private:
+    struct Item { size_t slot, index; std::vector<unsigned char> rgb; };
+    void run() {
+        for (;;) {
+            Item it;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [this] { return !q_.empty() || closed_; });
+                if (q_.empty()) return;
+                it = std::move(q_.front());
+                q_.pop_front();
+                cv_.notify_all();
+            }
+            results_[it.slot].done = save_frame(o_, it.index, it.rgb);
+        }
+    }
+    const Options& o_;
+    std::vector<FrameResult>& results_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Item> q_;
+    bool closed_ = false;
+    std::thread th_;
+};
+
 // One GPU renders the frames jobs[k] with k % stride == offset.
-void frame_worker(int device, const Options& o, const std::vector<DsrtTriangle>& tris,
-                  const std::vector<DsrtMaterial>& mats, const std::vector<FrameJob>& jobs,
+void frame_worker(int device, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
                   int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors) {
     dsrt_ctx* ctx = nullptr;
     if (dsrt_create(&ctx, device) != DSRT_OK) {
@@ -130,8 +205,7 @@ void frame_worker(int device, const Options& o, const std::vector<DsrtTriangle>&
         ++errors;
         return;
     }
-    if (dsrt_scene_upload(ctx, tris.data(), (int)tris.size(), mats.data(), (int)mats.size(),
-                          nullptr, 0, nullptr, 0, nullptr, 0) != DSRT_OK) {
+    if (upload(ctx, scene) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
         std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(ctx));
         ++errors;
@@ -146,9 +220,10 @@ void frame_worker(int device, const Options& o, const std::vector<DsrtTriangle>&
                   << " wide nodes, upload " << st.upload_ms << " ms)\n";
     }
     const DsrtRenderParams params = make_params(o);
-    std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+    FrameWriter writer(o, results);
     for (size_t k = (size_t)offset; k < jobs.size(); k += (size_t)stride) {
         const FrameJob& j = jobs[k];
+        std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
         DsrtCamera cam;
         dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
         int rc = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
@@ -163,20 +238,21 @@ void frame_worker(int device, const Options& o, const std::vector<DsrtTriangle>&
         dsrt_frame_stats(ctx, &fs);
         results[k].device_ms = fs.device_ms;
         results[k].rays = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
-        results[k].done = save_frame(o, j.index, rgb);
+        writer.push(k, j.index, std::move(rgb));
         std::lock_guard<std::mutex> l(g_print);
         char name[64];
         std::snprintf(name, sizeof(name), "frame_%04zu.png", j.index);
         std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << device << ", " << fs.device_ms << " ms, "
                   << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
     }
+    writer.finish();
     dsrt_destroy(ctx);
 }
 
 #ifdef DSRT_WITH_NCCL
 // One frame at a time, its samples split over the GPUs; one ncclReduce(sum) of the float
 // accumulation buffer to GPU 0, which tone-maps and writes the frame.
-int sample_sharded(const Options& o, const std::vector<DsrtTriangle>& tris, const std::vector<DsrtMaterial>& mats,
+int sample_sharded(const Options& o, const SceneData& scene,
                    const std::vector<FrameJob>& jobs, std::vector<FrameResult>& results) {
     const int G = o.gpus;
     std::vector<dsrt_ctx*> ctx(G, nullptr);
@@ -190,9 +266,7 @@ int sample_sharded(const Options& o, const std::vector<DsrtTriangle>& tris, cons
         std::atomic<int> err(0);
         for (int g = 0; g < G; ++g)
             th.emplace_back([&, g] {
-                if (dsrt_create(&ctx[g], g) != DSRT_OK ||
-                    dsrt_scene_upload(ctx[g], tris.data(), (int)tris.size(), mats.data(), (int)mats.size(),
-                                      nullptr, 0, nullptr, 0, nullptr, 0) != DSRT_OK) {
+                if (dsrt_create(&ctx[g], g) != DSRT_OK || upload(ctx[g], scene) != DSRT_OK) {
                     std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx[g]));
                     ++err;
                 }
@@ -202,9 +276,10 @@ int sample_sharded(const Options& o, const std::vector<DsrtTriangle>& tris, cons
     }
     if (errors) return 1;
     const DsrtRenderParams params = make_params(o);
-    std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+    FrameWriter writer(o, results);
     for (size_t k = 0; k < jobs.size(); ++k) {
         const FrameJob& j = jobs[k];
+        std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
         DsrtCamera cam;
         dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
         std::vector<std::thread> th;
@@ -235,10 +310,11 @@ int sample_sharded(const Options& o, const std::vector<DsrtTriangle>& tris, cons
         double mx = 0, total = 0;
         for (int g = 0; g < G; ++g) { mx = std::max(mx, ms[g]); total += rays[g]; }
         results[k].device_ms = mx; results[k].rays = total;
-        results[k].done = save_frame(o, j.index, rgb);
+        writer.push(k, j.index, std::move(rgb));
         std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, " << mx << " ms, "
                   << total / (mx * 1e3) << " Mrays/s]\n";
     }
+    writer.finish();
     for (int g = 0; g < G; ++g) { dsrt_destroy(ctx[g]); ncclCommDestroy(comm[g]); }
     return errors ? 1 : 0;
 }
@@ -257,17 +333,36 @@ int main(int argc, char** argv) {
     if (o.upscale) std::cout << "--upscale: the Real-ESRGAN post-process is outside this renderer; ignored.\n";
     const auto total_start = clk::now();
 
-    // The mesh is static in the model frame: generated (or, later, loaded) once.
+    // The mesh is static in the model frame: loaded (or generated) once, uploaded once per GPU.
     const auto t1 = clk::now();
-    std::vector<DsrtTriangle> tris((size_t)std::max(0, o.synthetic_tris));
-    std::vector<DsrtMaterial> mats(32);
-    const int nm = dsrt_synth_mesh((int)tris.size(), 1337u, o.diffuse_only ? 1 : 0, tris.data(), mats.data(), (int)mats.size());
-    if (nm < 0) { std::fprintf(stderr, "synthetic mesh generation failed\n"); return 1; }
-    mats.resize((size_t)nm);
+    SceneData scene;
+    std::string scene_desc;
+    {
+        dsrt_mesh* mesh = nullptr;
+        if (dsrt_mesh_load_obj(o.obj_path.c_str(), o.obj_scale, &mesh) == DSRT_OK) {
+            DsrtMeshView v;
+            dsrt_mesh_view(mesh, &v);
+            scene.tris.assign(v.triangles, v.triangles + v.num_triangles);
+            scene.mats.assign(v.materials, v.materials + v.num_materials);
+            scene.tex.assign(v.textures, v.textures + v.num_textures);
+            scene.pool.assign(v.texture_pool, v.texture_pool + v.texture_pool_floats);
+            scene_desc = std::to_string(v.num_triangles) + " triangles, " + std::to_string(v.num_materials) + " materials, " +
+                         std::to_string(v.num_textures) + " textures from " + o.obj_path;
+            if (v.skipped_faces) scene_desc += " (" + std::to_string(v.skipped_faces) + " triangles with bad indices dropped)";
+            dsrt_mesh_free(mesh);
+        } else {
+            scene.tris.resize((size_t)std::max(0, o.synthetic_tris));
+            scene.mats.resize(32);
+            const int nm = dsrt_synth_mesh((int)scene.tris.size(), 1337u, o.diffuse_only ? 1 : 0, scene.tris.data(),
+                                           scene.mats.data(), (int)scene.mats.size());
+            if (nm < 0) { std::fprintf(stderr, "synthetic mesh generation failed\n"); return 1; }
+            scene.mats.resize((size_t)nm);
+            scene_desc = o.obj_path + " not found: " + std::to_string(scene.tris.size()) + " synthetic triangles";
+        }
+    }
     const auto t2 = clk::now();
     std::cout << "Base ISS + material load time: "
-              << std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count() << " ms ("
-              << tris.size() << " synthetic triangles)\n";
+              << std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count() << " ms (" << scene_desc << ")\n";
 
     // Poses, or the reference's single default pose.
     std::vector<double> poses;
@@ -310,9 +405,10 @@ int main(int argc, char** argv) {
     std::vector<FrameResult> results(jobs.size());
     int rc = 0;
     const int G = std::max(1, o.gpus);
+    const auto render_start = clk::now();
     if (o.shard == "sample" && G > 1) {
 #ifdef DSRT_WITH_NCCL
-        rc = sample_sharded(o, tris, mats, jobs, results);
+        rc = sample_sharded(o, scene, jobs, results);
 #else
         std::fprintf(stderr, "--shard sample needs a build with NCCL\n");
         rc = 1;
@@ -321,7 +417,7 @@ int main(int argc, char** argv) {
         std::atomic<int> errors(0);
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g)
-            th.emplace_back(frame_worker, g, std::cref(o), std::cref(tris), std::cref(mats), std::cref(jobs), g, G,
+            th.emplace_back(frame_worker, g, std::cref(o), std::cref(scene), std::cref(jobs), g, G,
                             std::ref(results), std::ref(errors));
         for (auto& t : th) t.join();
         rc = errors ? 1 : 0;
@@ -329,6 +425,8 @@ int main(int argc, char** argv) {
 
     const auto total_end = clk::now();
     const double total_s = std::chrono::duration<double>(total_end - total_start).count();
+    // upload + BVH build + every frame rendered, read back and written (PPM + PNG) on all GPUs
+    const double render_wall_s = std::chrono::duration<double>(total_end - render_start).count();
     double rays = 0, ms = 0;
     size_t done = 0;
     for (const auto& r : results) { if (r.done) { ++done; rays += r.rays; ms += r.device_ms; } }
@@ -336,8 +434,11 @@ int main(int argc, char** argv) {
     if (done) std::cout << "Frames: " << done << ", device time " << ms << " ms, " << rays / (ms * 1e3) << " Mrays/s per GPU-time\n";
     if (!o.stats_json.empty()) {
         if (FILE* f = std::fopen(o.stats_json.c_str(), "w")) {
-            std::fprintf(f, "{\"frames\": %zu, \"gpus\": %d, \"shard\": \"%s\", \"total_s\": %.3f, \"device_ms\": %.3f, \"rays\": %.0f}\n",
-                         done, G, o.shard.c_str(), total_s, ms, rays);
+            std::fprintf(f, "{\"frames\": %zu, \"gpus\": %d, \"shard\": \"%s\", \"total_s\": %.3f, \"render_wall_s\": %.3f, "
+                            "\"frames_per_s\": %.4f, \"device_ms\": %.3f, \"rays\": %.0f, \"width\": %d, \"height\": %d, \"spp\": %d, "
+                            "\"max_depth\": %d, \"triangles\": %zu, \"png\": %s}\n",
+                         done, G, o.shard.c_str(), total_s, render_wall_s, render_wall_s > 0 ? done / render_wall_s : 0.0, ms, rays,
+                         o.width, o.height, o.spp, o.max_depth, scene.tris.size(), o.png ? "true" : "false");
             std::fclose(f);
         }
     }
