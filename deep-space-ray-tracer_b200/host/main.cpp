@@ -123,6 +123,15 @@ struct FrameResult {
     bool done = false;
 };
 
+// Wall-clock split of a run: what is paid once per GPU (CUDA context, scene upload, BVH build,
+// work-memory allocation inside the first frame) versus the steady frame loop.
+struct SetupTimes {
+    double create_s = 0, upload_s = 0, first_frame_s = 0, loop_s = 0, teardown_s = 0;
+};
+inline double seconds_since(std::chrono::high_resolution_clock::time_point t0) {
+    return std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+}
+
 const float kSunRadiance[3] = {100000.0f, 95000.0f, 90000.0f};   // gpu_scene_builder.cpp:598
 
 DsrtRenderParams make_params(const Options& o) {
@@ -197,14 +206,17 @@ private:
 
 // One GPU renders the frames jobs[k] with k % stride == offset.
 void frame_worker(int device, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
-                  int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors) {
+                  int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors, SetupTimes& times) {
     dsrt_ctx* ctx = nullptr;
+    auto t0 = std::chrono::high_resolution_clock::now();
     if (dsrt_create(&ctx, device) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
         std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(nullptr));
         ++errors;
         return;
     }
+    times.create_s = seconds_since(t0);
+    t0 = std::chrono::high_resolution_clock::now();
     if (upload(ctx, scene) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
         std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(ctx));
@@ -212,6 +224,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
         dsrt_destroy(ctx);
         return;
     }
+    times.upload_s = seconds_since(t0);
     {
         DsrtSceneStats st;
         dsrt_scene_stats(ctx, &st);
@@ -221,6 +234,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
     }
     const DsrtRenderParams params = make_params(o);
     FrameWriter writer(o, results);
+    t0 = std::chrono::high_resolution_clock::now();
     for (size_t k = (size_t)offset; k < jobs.size(); k += (size_t)stride) {
         const FrameJob& j = jobs[k];
         std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
@@ -228,6 +242,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
         dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
         int rc = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
         if (rc == DSRT_OK) rc = dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb.data(), rgb.size());
+        if (k == (size_t)offset) times.first_frame_s = seconds_since(t0);
         if (rc != DSRT_OK) {
             std::lock_guard<std::mutex> l(g_print);
             std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, device, dsrt_last_error(ctx));
@@ -246,7 +261,10 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
                   << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
     }
     writer.finish();
+    times.loop_s = seconds_since(t0);
+    t0 = std::chrono::high_resolution_clock::now();
     dsrt_destroy(ctx);
+    times.teardown_s = seconds_since(t0);
 }
 
 #ifdef DSRT_WITH_NCCL
@@ -405,6 +423,7 @@ int main(int argc, char** argv) {
     std::vector<FrameResult> results(jobs.size());
     int rc = 0;
     const int G = std::max(1, o.gpus);
+    std::vector<SetupTimes> times((size_t)G);
     const auto render_start = clk::now();
     if (o.shard == "sample" && G > 1) {
 #ifdef DSRT_WITH_NCCL
@@ -418,7 +437,7 @@ int main(int argc, char** argv) {
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g)
             th.emplace_back(frame_worker, g, std::cref(o), std::cref(scene), std::cref(jobs), g, G,
-                            std::ref(results), std::ref(errors));
+                            std::ref(results), std::ref(errors), std::ref(times[(size_t)g]));
         for (auto& t : th) t.join();
         rc = errors ? 1 : 0;
     }
@@ -430,15 +449,26 @@ int main(int argc, char** argv) {
     double rays = 0, ms = 0;
     size_t done = 0;
     for (const auto& r : results) { if (r.done) { ++done; rays += r.rays; ms += r.device_ms; } }
-    std::cout << "\nTotal runtime: " << (long long)total_s << " s\n";
+    SetupTimes worst;
+    for (const auto& t : times) {
+        worst.create_s = std::max(worst.create_s, t.create_s); worst.upload_s = std::max(worst.upload_s, t.upload_s);
+        worst.first_frame_s = std::max(worst.first_frame_s, t.first_frame_s); worst.loop_s = std::max(worst.loop_s, t.loop_s);
+        worst.teardown_s = std::max(worst.teardown_s, t.teardown_s);
+    }
+    std::cout << "\nPer-GPU wall clock (max over GPUs): context " << worst.create_s << " s, scene upload + BVH " << worst.upload_s
+              << " s, first frame " << worst.first_frame_s << " s, frame loop " << worst.loop_s << " s, teardown " << worst.teardown_s << " s\n";
+    std::cout << "Total runtime: " << (long long)total_s << " s\n";
     if (done) std::cout << "Frames: " << done << ", device time " << ms << " ms, " << rays / (ms * 1e3) << " Mrays/s per GPU-time\n";
     if (!o.stats_json.empty()) {
         if (FILE* f = std::fopen(o.stats_json.c_str(), "w")) {
             std::fprintf(f, "{\"frames\": %zu, \"gpus\": %d, \"shard\": \"%s\", \"total_s\": %.3f, \"render_wall_s\": %.3f, "
                             "\"frames_per_s\": %.4f, \"device_ms\": %.3f, \"rays\": %.0f, \"width\": %d, \"height\": %d, \"spp\": %d, "
-                            "\"max_depth\": %d, \"triangles\": %zu, \"png\": %s}\n",
+                            "\"max_depth\": %d, \"triangles\": %zu, \"png\": %s, \"context_s\": %.3f, \"upload_s\": %.3f, \"first_frame_s\": %.3f, "
+                            "\"frame_loop_s\": %.3f, \"teardown_s\": %.3f, \"loop_frames_per_s\": %.4f}\n",
                          done, G, o.shard.c_str(), total_s, render_wall_s, render_wall_s > 0 ? done / render_wall_s : 0.0, ms, rays,
-                         o.width, o.height, o.spp, o.max_depth, scene.tris.size(), o.png ? "true" : "false");
+                         o.width, o.height, o.spp, o.max_depth, scene.tris.size(), o.png ? "true" : "false",
+                         worst.create_s, worst.upload_s, worst.first_frame_s, worst.loop_s, worst.teardown_s,
+                         worst.loop_s > 0 ? done / worst.loop_s : 0.0);
             std::fclose(f);
         }
     }
