@@ -308,7 +308,7 @@ class Context:
 
     def download_bvh(self):
         st = self.scene_stats()
-        nodes = np.zeros((st.num_wide_nodes, 20), dtype=np.uint32)
+        nodes = np.zeros((st.num_wide_nodes, 24), dtype=np.uint32)      # 96-byte nodes (csrc/bvh8.cuh)
         recs = np.zeros((st.num_triangles, 12), dtype=np.float32)
         self._ck(lib.dsrt_scene_download(self._h, nodes.ctypes.data, nodes.nbytes, recs.ctypes.data, recs.nbytes))
         return nodes, recs

@@ -322,7 +322,7 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
     st.build_ms = ctx->bvh.build_ms;
     st.sah_cost = ctx->bvh.sah_cost;
     for (int a = 0; a < 3; ++a) { st.scene_lo[a] = ctx->bvh.scene_lo[a]; st.scene_hi[a] = ctx->bvh.scene_hi[a]; }
-    st.node_bytes = (uint64_t)ctx->bvh.num_nodes * 80u;
+    st.node_bytes = (uint64_t)ctx->bvh.num_nodes * (16u * kNodeWords);
     st.tri_bytes = (uint64_t)ntris * 48u;
     ctx->sstats = st;
     ctx->have_scene = true;
@@ -361,7 +361,7 @@ extern "C" int dsrt_scene_download(dsrt_ctx* ctx, void* nodes, size_t node_bytes
     if (!ctx) return DSRT_EINVAL;
     if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "no scene uploaded");
     CK(cudaSetDevice(ctx->device));
-    const size_t nb = (size_t)ctx->bvh.num_nodes * 80u, tb = (size_t)ctx->bvh.num_tris * 48u;
+    const size_t nb = (size_t)ctx->bvh.num_nodes * (16u * kNodeWords), tb = (size_t)ctx->bvh.num_tris * 48u;
     if ((nodes && node_bytes < nb) || (tri_records && tri_bytes < tb))
         return fail(ctx, DSRT_EINVAL, "dsrt_scene_download: need %zu node bytes and %zu triangle bytes", nb, tb);
     if (nodes && nb) CK(cudaMemcpyAsync(nodes, ctx->bvh.nodes, nb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -4,7 +4,7 @@
 // traversal bvh_hit_closest / bbox_hit / hit_triangle_index
 // (/root/reference/src/gpu_render.cu:387-473, 285-315, 322-380).
 //
-// Node (80 bytes = five 16-byte words, fetched with five 128-bit loads):
+// Node (96 bytes = six 16-byte words, fetched with six 128-bit loads):
 //   w0: float p.x, p.y, p.z            quantisation origin (node box minimum, padded)
 //       u32   ex | ey<<8 | ez<<16 | imask<<24     biased exponents of the grid step per axis,
 //                                                  imask bit s = child slot s is an inner node
@@ -12,14 +12,27 @@
 //                        ordered by slot)
 //       u32 tri_base     index of the first triangle record of this node's leaf children
 //       u8  meta[8]      slot s: 0 = empty; inner: 0x20 | (24+s); leaf: unary(count)<<5 | offset
+//                        (the builder's description of the slot; the traversal reads w5 instead)
 //   w2: u8 qlo_x[8], qlo_y[8]
 //   w3: u8 qlo_z[8], qhi_x[8]
 //   w4: u8 qhi_y[8], qhi_z[8]
+//   w5: bf16 tri_weight[8]   slot s: the leaf child's triangle bits unary(count) << offset as a
+//                            number (1, 3 or 7 times 2^offset -- two mantissa bits, so exact in
+//                            bfloat16); 0 for inner and empty slots
 // Child box = p + q * 2^(e-127) per axis, conservative by construction (bvh_build.cu).
-// Children sit in slots chosen from their octant relative to the node centre, so visiting
-// set bits of `(24+slot) ^ octant-inverse` from the top approximates front-to-back order
+// Children sit in slots chosen from their octant relative to the node centre, so visiting the
+// hit inner children in decreasing `slot ^ octant-inverse` approximates front-to-back order
 // without sorting (Ylitie, Karras, Laine: "Efficient incoherent ray traversal on GPUs
 // through compressed wide BVHs", HPG 2017 -- algorithm restated, code written here).
+//
+// Hit masks are summed, not shifted together: the ALU pipe (PRMT, FMNMX, LOP3, SHF, SEL) is what
+// bounds this traversal on B200 (profiles/r01_n: ALU 70 % busy, FMA 24 %, top stall
+// math_pipe_throttle) and assembling `bits << index` per child cost ~8 ALU instructions for each
+// of the eight slots.  Instead every hit child adds two floats on the FMA pipe under its hit
+// predicate: 2^slot into an accumulator that starts at 2^23 (its low mantissa byte is then the
+// 8-bit slot mask) and its tri_weight into a second one (sums of disjoint bits below 2^24 are
+// exact).  The slot mask, restricted to inner children, goes through a 2 KB shared-memory table
+// that applies the `slot ^ octant-inverse` permutation.
 //
 // Triangle record (48 bytes, three 128-bit loads), stored in leaf order:
 //   a: v0.xyz, bits(index in the uploaded triangle array)
@@ -36,7 +49,7 @@
 
 namespace dsrt {
 
-constexpr int kNodeWords = 5;          // uint4 words per node
+constexpr int kNodeWords = 6;          // uint4 words per node
 constexpr int kTriWords = 3;           // float4 words per triangle record
 constexpr int kMaxLeafTris = 3;
 constexpr int kSmemStack = 8;          // stack entries per thread kept in shared memory
@@ -155,19 +168,37 @@ __device__ __forceinline__ SlabAxis slab_axis(uint32_t ebyte, float p, float o, 
     return s;
 }
 
-// Intersects the eight child boxes of one node; returns the hit mask (bits 24..31 inner
-// children in traversal-priority order, bits 0..23 triangles).
+// Table of the octant permutation: entry [o][m] = the 8-bit mask m with bit s moved to bit s ^ o.
+// 2 KB per block, filled by the whole block before its first traversal step.
+constexpr int kPermTableBytes = 8 * 256;
+__device__ __forceinline__ void fill_perm_table(uint8_t* table, int nthreads) {
+    for (int i = threadIdx.x; i < kPermTableBytes; i += nthreads) {
+        const uint32_t o = (uint32_t)i >> 8, m = (uint32_t)i & 0xFFu;
+        uint32_t r = 0u;
+#pragma unroll
+        for (uint32_t sl = 0; sl < 8u; ++sl)
+            if ((m >> sl) & 1u) r |= 1u << (sl ^ o);
+        table[i] = (uint8_t)r;
+    }
+    __syncthreads();
+}
+
+// Intersects the eight child boxes of one node.  Returns the hit inner children as an 8-bit mask in
+// slot order (still to be permuted into traversal order) and sets `tri_hits` to the 24-bit mask of
+// the triangles of the hit leaf children.
 __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, uint32_t node_index,
                                               float ox, float oy, float oz,
                                               float idx, float idy, float idz,
-                                              float tmin, float tmax, uint32_t octinv4, uint32_t one,
-                                              uint32_t& child_base, uint32_t& tri_base, uint32_t& imask) {
+                                              float tmin, float tmax, uint32_t one,
+                                              uint32_t& child_base, uint32_t& tri_base, uint32_t& imask,
+                                              uint32_t& tri_hits) {
     const uint4* np = nodes + (size_t)node_index * kNodeWords;
     const uint4 w0 = __ldg(np + 0);
     const uint4 w1 = __ldg(np + 1);
     const uint4 w2 = __ldg(np + 2);
     const uint4 w3 = __ldg(np + 3);
     const uint4 w4 = __ldg(np + 4);
+    const uint4 w5 = __ldg(np + 5);
 
     const uint32_t ew = w0.w;
     imask = ew >> 24;
@@ -178,22 +209,18 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
     const SlabAxis Y = slab_axis((ew >> 8) & 0xFFu, __uint_as_float(w0.y), oy, idy);
     const SlabAxis Z = slab_axis((ew >> 16) & 0xFFu, __uint_as_float(w0.z), oz, idz);
 
-    uint32_t hitmask = 0;
+    float slot_acc = 8388608.0f;       // 2^23: the slots hit end up in the low mantissa byte
+    float tri_acc = 0.0f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const uint32_t meta4 = h ? w1.w : w1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-
         const uint32_t qlox = h ? w2.y : w2.x, qloy = h ? w2.w : w2.z;
         const uint32_t qloz = h ? w3.y : w3.x, qhix = h ? w3.w : w3.z;
         const uint32_t qhiy = h ? w4.y : w4.x, qhiz = h ? w4.w : w4.z;
         const uint32_t nx = idx < 0.0f ? qhix : qlox, fx = idx < 0.0f ? qlox : qhix;
         const uint32_t ny = idy < 0.0f ? qhiy : qloy, fy = idy < 0.0f ? qloy : qhiy;
         const uint32_t nz = idz < 0.0f ? qhiz : qloz, fz = idz < 0.0f ? qloz : qhiz;
-#define DSRT_CHILD(J)                                                                      \
+        const uint32_t wa = h ? w5.z : w5.x, wb = h ? w5.w : w5.y;       // weights of slots 4h..4h+1, 4h+2..4h+3
+#define DSRT_CHILD(J, WEIGHT)                                                              \
         {                                                                                  \
             const float t0x = fmaf(plane_byte<J>(nx, one), X.A, X.B0);                     \
             const float t0y = fmaf(plane_byte<J>(ny, one), Y.A, Y.B0);                     \
@@ -204,15 +231,15 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));                   \
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));                   \
             if (cmin <= cmax) {                                                            \
-                const uint32_t bits = (child_bits4 >> (8 * J)) & 0xFFu;                    \
-                const uint32_t idxb = (bit_index4 >> (8 * J)) & 0xFFu;                     \
-                hitmask |= bits << idxb;                                                   \
+                slot_acc += (float)(1 << (4 * h + J));                                     \
+                tri_acc += __uint_as_float(WEIGHT);                                        \
             }                                                                              \
         }
-        DSRT_CHILD(0) DSRT_CHILD(1) DSRT_CHILD(2) DSRT_CHILD(3)
+        DSRT_CHILD(0, wa << 16) DSRT_CHILD(1, wa & 0xFFFF0000u) DSRT_CHILD(2, wb << 16) DSRT_CHILD(3, wb & 0xFFFF0000u)
 #undef DSRT_CHILD
     }
-    return hitmask;
+    tri_hits = __float2uint_rz(tri_acc);
+    return __float_as_uint(slot_acc) & imask;
 }
 
 // Traversal state of one ray, kept in registers by a persistent thread.  `step` advances the
@@ -227,6 +254,7 @@ struct LaneTrav {
     uint32_t octinv;
     uint2 ngroup;
     uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
+    const uint8_t* perm;          // the block's octant-permutation table (fill_perm_table), shared memory
     bool any_hit;
 
     __device__ __forceinline__ void init(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_,
@@ -252,11 +280,11 @@ struct LaneTrav {
             const uint32_t rel = __popc(ngroup.y & 0xFFu & ((1u << slot) - 1u));
             const uint32_t node_index = ngroup.x + rel;
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
-            uint32_t child_base, tri_base, imask;
-            const uint32_t hm = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
-                                          octinv * 0x01010101u, one, child_base, tri_base, imask);
-            ngroup = make_uint2(child_base, (hm & 0xFF000000u) | imask);
-            tgroup = make_uint2(tri_base, hm & 0x00FFFFFFu);
+            uint32_t child_base, tri_base, imask, tri_hits;
+            const uint32_t slots = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
+                                             one, child_base, tri_base, imask, tri_hits);
+            ngroup = make_uint2(child_base, ((uint32_t)perm[(octinv << 8) + slots] << 24) | imask);
+            tgroup = make_uint2(tri_base, tri_hits);
         } else {
             tgroup = ngroup;
             ngroup = make_uint2(0u, 0u);

@@ -396,6 +396,7 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
     const float p3[3] = {px, py, pz};
 
     uint32_t meta[8];
+    uint32_t weight[8];        // bfloat16 bits of unary(count) << offset for leaf children, else 0 (bvh8.cuh: w5)
     uint32_t qlo[3][8], qhi[3][8];
     int rank = 0, tri_off = 0;
     float sah = half_area(nlo, nhi) * (float)nch * 0.5f;    // cost of testing this node's boxes
@@ -403,6 +404,7 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
         int k = slot_child[s];
         if (k < 0) {
             meta[s] = 0;
+            weight[s] = 0;
             for (int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }
             continue;
         }
@@ -432,10 +434,13 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
                 rec[2] = make_float4(__fsub_rn(tp[6], v0x), __fsub_rn(tp[7], v0y), __fsub_rn(tp[8], v0z), 0.f);
             }
             meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_off;
+            // (2^cnt - 1) * 2^tri_off = 1.0, 1.5 or 1.75 times 2^(tri_off + cnt - 1): the top 16 bits of that float
+            weight[s] = ((uint32_t)(127 + tri_off + cnt - 1) << 7) | (cnt == 1 ? 0x00u : cnt == 2 ? 0x40u : 0x60u);
             tri_off += cnt;
             sah += half_area(clo[k], chi[k]) * (float)cnt;
         } else {
             meta[s] = 0x20u | (24u + (uint32_t)s);
+            weight[s] = 0;
             items_out[item_base + rank] = make_int2(node_c, (int)(child_base + rank));
             ++rank;
         }
@@ -451,6 +456,8 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
     np[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
     np[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     np[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    np[5] = make_uint4(weight[0] | (weight[1] << 16), weight[2] | (weight[3] << 16),
+                       weight[4] | (weight[5] << 16), weight[6] | (weight[7] << 16));
 }
 
 // ---- per-triangle shading records (indexed by the uploaded triangle index) ---------------

@@ -10,7 +10,7 @@
 namespace dsrt {
 
 struct Bvh8 {
-    uint4* nodes = nullptr;          // num_nodes x 5 words (80 B each), breadth-first
+    uint4* nodes = nullptr;          // num_nodes x 6 words (96 B each), breadth-first
     float4* tri_records = nullptr;   // num_tris x 3 words (48 B each), leaf order
     float4* shade_records = nullptr; // num_tris x 3 words, indexed by uploaded triangle index
     float4* uv_records = nullptr;    // num_tris x 2 words, only when textures are present

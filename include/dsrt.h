@@ -53,7 +53,7 @@ void* dsrt_stream(dsrt_ctx* ctx);
 /* ---- scene: replaces build_gpu_scene()'s flatten + CPU BVH + 7 uploads ----------------
  * Copies the reference-layout arrays to the device and builds, on the GPU, a Morton-sorted
  * LBVH that is collapsed by surface area into an 8-wide BVH with quantised child boxes
- * (80-byte nodes) and 48-byte triangle records in leaf order.  Done once per mesh, not per
+ * (96-byte nodes) and 48-byte triangle records in leaf order.  Done once per mesh, not per
  * frame.  Spheres (never instantiated by the reference's main(), but part of GPUScene) are
  * intersected by a brute-force loop after the triangles exactly as the reference's scene_hit
  * does (gpu_render.cu:530-546); emissive ones switch the diffuse bounce to the reference's
@@ -74,7 +74,7 @@ int dsrt_scene_upload_device(dsrt_ctx* ctx,
                              const DsrtTextureHeader* textures_device, int ntextures,
                              const float* texture_pool_device, int texture_pool_floats);
 int dsrt_scene_stats(dsrt_ctx* ctx, DsrtSceneStats* out);
-/* Debug/verification: copies the wide BVH back (80-byte nodes, 48-byte triangle records). */
+/* Debug/verification: copies the wide BVH back (96-byte nodes, 48-byte triangle records). */
 int dsrt_scene_download(dsrt_ctx* ctx, void* nodes, size_t node_bytes, void* tri_records, size_t tri_bytes);
 
 /* ---- render: replaces gpu_render_scene() ---------------------------------------------

@@ -103,7 +103,7 @@ typedef struct DsrtRenderParams {
 /* What one dsrt_scene_upload produced. */
 typedef struct DsrtSceneStats {
     int32_t num_triangles;
-    int32_t num_wide_nodes;      /* 80-byte BVH8 nodes */
+    int32_t num_wide_nodes;      /* 96-byte BVH8 nodes */
     int32_t num_levels;          /* levels of the wide tree */
     int32_t max_leaf_tris;
     float   build_ms;            /* device time of the whole build (CUDA events) */

@@ -1,11 +1,12 @@
 """Host-side invariants of the GPU-built wide BVH (layout in csrc/bvh8.cuh).
 
-Decodes the downloaded 80-byte nodes and 48-byte triangle records and checks:
+Decodes the downloaded 96-byte nodes and 48-byte triangle records and checks:
   * every uploaded triangle index appears in exactly one leaf record,
   * v0 / e1 / e2 of each record equal the uploaded vertices (e = one fp32 subtraction),
   * every leaf child's decoded (de-quantised) box contains its triangles,
   * every inner child's decoded box contains the whole subtree below it,
-  * inner children are contiguous and ordered by slot; meta bytes are well formed.
+  * inner children are contiguous and ordered by slot; meta bytes are well formed,
+  * the bfloat16 triangle weights the traversal sums (word 5) equal unary(count) << offset.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ def _bytes(word):
 
 
 def decode_node(n):
-    """n: 20 uint32 words -> dict."""
+    """n: 24 uint32 words -> dict."""
     p = n[0:3].view(np.float32).astype(np.float64)
     ew = int(n[3])
     e = [(ew >> (8 * k)) & 0xFF for k in range(3)]
@@ -33,7 +34,10 @@ def decode_node(n):
     q["hiz"] = _bytes(n[18]) + _bytes(n[19])
     lo = np.stack([np.array(q["lox"]), np.array(q["loy"]), np.array(q["loz"])], 1) * scale + p
     hi = np.stack([np.array(q["hix"]), np.array(q["hiy"]), np.array(q["hiz"])], 1) * scale + p
-    return dict(p=p, imask=imask, child_base=int(n[4]), tri_base=int(n[5]), meta=meta, lo=lo, hi=hi)
+    # word 5: eight bfloat16 numbers = the top halves of float32 bit patterns
+    wbits = np.array([(int(n[20 + s // 2]) >> (16 * (s % 2))) & 0xFFFF for s in range(8)], np.uint32) << 16
+    weight = wbits.view(np.float32).astype(np.float64)
+    return dict(p=p, imask=imask, child_base=int(n[4]), tri_base=int(n[5]), meta=meta, lo=lo, hi=hi, weight=weight)
 
 
 def check_bvh(nodes: np.ndarray, recs: np.ndarray, tris: np.ndarray) -> dict:
@@ -79,15 +83,18 @@ def check_bvh(nodes: np.ndarray, recs: np.ndarray, tris: np.ndarray) -> dict:
             inner = (d["imask"] >> s) & 1
             if m == 0:
                 assert not inner
+                assert d["weight"][s] == 0.0, "empty slot carries no triangle weight"
                 continue
             nchild += 1
             if inner:
                 assert m == (0x20 | (24 + s)), f"inner meta of slot {s}"
+                assert d["weight"][s] == 0.0, "inner slot carries no triangle weight"
                 stack.append((d["child_base"] + rank, depth + 1))
                 rank += 1
             else:
                 cnt_bits = m >> 5
                 assert cnt_bits in (1, 3, 7), "unary triangle count"
+                assert d["weight"][s] == float(cnt_bits << (m & 31)), f"triangle weight of slot {s}"
         stats["children_hist"][nchild] += 1
     assert visited.all(), "all nodes reachable"
 
