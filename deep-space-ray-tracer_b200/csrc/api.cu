@@ -67,6 +67,7 @@ struct dsrt_ctx {
     DsrtFrameStats fstats{};
     int stage_timing = 0;
     int spb_override = 0;
+    int builder = DSRT_BUILDER_PLOC;   // binary-tree stage of the BVH build (bvh_build.h)
     int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
     cudaEvent_t ev_frame[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
@@ -207,6 +208,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     }
     launch_dims(&ctx->dims, device);
     if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);      // tuning experiments only
+    if (const char* e = getenv("DSRT_BVH_BUILDER")) ctx->builder = strcmp(e, "lbvh") == 0 ? DSRT_BUILDER_LBVH : DSRT_BUILDER_PLOC;
     *out = ctx;
     return DSRT_OK;
 }
@@ -312,7 +314,7 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
             cudaEventElapsedTime(&st.upload_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
         }
         char msg[256] = "";
-        int rc = build_bvh8(ctx->stream, from_device ? tris : d_raw, ntris, ntextures > 0, &ctx->bvh, msg, sizeof(msg));
+        int rc = build_bvh8(ctx->stream, from_device ? tris : d_raw, ntris, ntextures > 0, ctx->builder, &ctx->bvh, msg, sizeof(msg));
         if (d_raw) cudaFree(d_raw);
         if (rc != 0) return fail(ctx, DSRT_ECUDA, "BVH build failed: %s", msg);
     }

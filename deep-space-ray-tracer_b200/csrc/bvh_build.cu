@@ -7,8 +7,14 @@
 //   1. triangle bounds + scene bounds            (k_tri_bounds)
 //   2. 63-bit Morton codes of box centres        (k_morton)
 //   3. radix sort (cub::DeviceRadixSort)
-//   4. binary radix tree, Karras 2012            (k_hierarchy)
-//   5. bottom-up box refit with atomic flags     (k_refit)
+//   4. binary tree over the sorted triangles, one of
+//        a. PLOC -- parallel locally-ordered clustering (Meister & Bittner 2018, algorithm
+//           restated): every cluster looks +-kPlocRadius positions along the Morton order for the
+//           partner that minimises the merged surface area, mutual nearest neighbours merge,
+//           the cluster list is compacted, repeat until one cluster is left
+//           (k_ploc_nearest, k_ploc_mark, cub::DeviceScan, k_ploc_merge) -- the default;
+//        b. the binary radix tree of Karras 2012 (k_hierarchy) -- DSRT_BVH_BUILDER=lbvh
+//   5. bottom-up pass with atomic flags: boxes, triangle counts and the dynamic programme below (k_refit)
 //   6. top-down collapse, one level per launch:  (k_collapse_level)
 //        each binary node expands into <= 8 children along the cost-optimal cut found by a
 //        bottom-up dynamic programme over the surface-area heuristic (in k_refit),
@@ -21,6 +27,7 @@
 #include "bvh_build.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cfloat>
 #include <cstdio>
@@ -139,8 +146,7 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
 }
 
 __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n,
-                            int2* __restrict__ children, int* __restrict__ parent,
-                            int2* __restrict__ range) {
+                            int2* __restrict__ children, int* __restrict__ parent) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -163,10 +169,110 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n,
     int left = (first == gamma) ? (n - 1 + gamma) : gamma;
     int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
     children[i] = make_int2(left, right);
-    range[i] = make_int2(first, last);
     parent[left] = i;
     parent[right] = i;
     if (i == 0) parent[0] = -1;
+}
+
+// ---- PLOC: agglomerative clustering along the Morton order ------------------------------------
+// Node ids as for the radix tree: leaf k (k-th triangle of the sorted order) is n-1+k; inner nodes
+// are handed out downwards from n-2, so that the last merge -- the root -- is node 0.
+// Ties in the merged area are broken towards the lower position, which guarantees that the
+// globally cheapest pair is mutual (so every round merges at least one pair) and makes the tree,
+// and with it every frame, reproducible from run to run.
+constexpr int kPlocRadius = 16;
+
+__device__ __forceinline__ float union_half_area(float4 l0, float4 h0, float4 l1, float4 h1) {
+    const float dx = fmaxf(h0.x, h1.x) - fminf(l0.x, l1.x);
+    const float dy = fmaxf(h0.y, h1.y) - fminf(l0.y, l1.y);
+    const float dz = fmaxf(h0.z, h1.z) - fminf(l0.z, l1.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_leaves(const uint32_t* __restrict__ vals, const float4* __restrict__ tlo,
+                              const float4* __restrict__ thi, int n,
+                              float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ clusters) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t tri = vals[k];
+    blo[n - 1 + k] = tlo[tri];
+    bhi[n - 1 + k] = thi[tri];
+    clusters[k] = n - 1 + k;
+}
+
+constexpr int kPlocThreads = 256;
+__global__ void __launch_bounds__(kPlocThreads)
+k_ploc_nearest(const int* __restrict__ clusters, int m, const float4* __restrict__ blo,
+               const float4* __restrict__ bhi, int* __restrict__ nearest) {
+    // the boxes of this block's window [base - R, base + T + R) staged in shared memory
+    __shared__ float4 s_lo[kPlocThreads + 2 * kPlocRadius];
+    __shared__ float4 s_hi[kPlocThreads + 2 * kPlocRadius];
+    const int base = blockIdx.x * kPlocThreads;
+    for (int t = threadIdx.x; t < kPlocThreads + 2 * kPlocRadius; t += kPlocThreads) {
+        const int j = base - kPlocRadius + t;
+        if (j >= 0 && j < m) {
+            const int c = clusters[j];
+            s_lo[t] = __ldg(&blo[c]);
+            s_hi[t] = __ldg(&bhi[c]);
+        }
+    }
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    if (i >= m) return;
+    const float4 l = s_lo[threadIdx.x + kPlocRadius], h = s_hi[threadIdx.x + kPlocRadius];
+    float best = FLT_MAX;
+    int bj = -1;
+    const int j0 = max(0, i - kPlocRadius), j1 = min(m - 1, i + kPlocRadius);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const int t = j - base + kPlocRadius;
+        const float a = union_half_area(l, h, s_lo[t], s_hi[t]);
+        if (a < best) { best = a; bj = j; }        // ascending j and a strict test: lowest position wins ties
+    }
+    nearest[i] = bj;
+}
+
+// flags[i]: low word 1 = position i survives the round (it is not the upper half of a merging
+// pair), high word 1 = position i is the lower half of a merging pair and creates the new node.
+__global__ void k_ploc_mark(const int* __restrict__ nearest, int m, unsigned long long* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nearest[i];
+    const bool mutual = j >= 0 && nearest[j] == i;
+    const unsigned long long keep = (mutual && j < i) ? 0ull : 1ull;
+    const unsigned long long lead = (mutual && i < j) ? 1ull : 0ull;
+    flags[i] = keep | (lead << 32);
+}
+
+// counters[0] = clusters left, counters[1] = next inner node id (counts down).
+__global__ void k_ploc_merge(const int* __restrict__ clusters, const int* __restrict__ nearest, int m,
+                             const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan,
+                             int next_id, int2* __restrict__ children, int* __restrict__ parent,
+                             float4* __restrict__ blo, float4* __restrict__ bhi,
+                             int* __restrict__ clusters_out, int* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long f = flags[i], sc = scan[i];
+    const int pos = (int)(sc & 0xFFFFFFFFull), rank = (int)(sc >> 32);
+    if (i == m - 1) {
+        counters[0] = pos + (int)(f & 1ull);
+        counters[1] = next_id - (rank + (int)(f >> 32));
+    }
+    if ((f & 1ull) == 0ull) return;
+    const int c = clusters[i];
+    if (f >> 32) {
+        const int d = clusters[nearest[i]];
+        const int id = next_id - rank;
+        children[id] = make_int2(c, d);
+        parent[c] = id;
+        parent[d] = id;
+        const float4 l0 = blo[c], h0 = bhi[c], l1 = blo[d], h1 = bhi[d];
+        blo[id] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+        bhi[id] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        clusters_out[pos] = id;
+    } else {
+        clusters_out[pos] = c;
+    }
 }
 
 // ---- bottom-up refit + optimal wide-node assignment ------------------------------------------
@@ -189,7 +295,7 @@ __device__ __forceinline__ float box_half_area(float4 l, float4 h) {
 __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restrict__ tlo,
                         const float4* __restrict__ thi, int n,
                         const int2* __restrict__ children, const int* __restrict__ parent,
-                        const int2* __restrict__ range,
+                        int* __restrict__ count,
                         float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags,
                         float* __restrict__ cost, uint32_t* __restrict__ dec) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,6 +305,7 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
     int node = n - 1 + k;
     blo[node] = l;
     bhi[node] = h;
+    count[node] = 1;
     {
         const float c = box_half_area(l, h) * kCostPrim;
         float* cn = cost + (size_t)node * 8;
@@ -224,8 +331,8 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
             cr[i] = __ldcg(&cost[(size_t)ch.y * 8 + i]);
         }
         const float area = box_half_area(l, h);
-        const int2 r = range[p];
-        const int count = r.y - r.x + 1;
+        const int cnt = __ldcg(&count[ch.x]) + __ldcg(&count[ch.y]);
+        count[p] = cnt;
         float dist[9];
         uint32_t kbest[9];
         for (int j = 2; j <= 8; ++j) {
@@ -241,7 +348,7 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
         }
         uint32_t d = kbest[8] << 24;
         float cp[8];
-        const float c_leaf = count <= kMaxLeafTris ? area * (float)count * kCostPrim : FLT_MAX;
+        const float c_leaf = cnt <= kMaxLeafTris ? area * (float)cnt * kCostPrim : FLT_MAX;
         const float c_wide = area * kCostNode + dist[8];
         if (c_leaf <= c_wide) { cp[1] = c_leaf; } else { cp[1] = c_wide; d |= 1u << 3; }
         for (int i = 2; i <= 7; ++i) {
@@ -259,7 +366,7 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
 struct CollapseArgs {
     int n;                         // triangles
     const int2* children;
-    const int2* range;
+    const int* count;              // triangles below each binary node
     const float4* blo;
     const float4* bhi;
     const uint32_t* dec;           // per binary node: decisions of the dynamic programme (k_refit)
@@ -279,9 +386,22 @@ __device__ __forceinline__ float half_area(float4 l, float4 h) {
 }
 
 __device__ __forceinline__ int subtree_count(const CollapseArgs& A, int node) {
-    if (node >= A.n - 1) return 1;
-    int2 r = A.range[node];
-    return r.y - r.x + 1;
+    return node >= A.n - 1 ? 1 : A.count[node];
+}
+
+// The (at most kMaxLeafTris) sorted positions below `node`, left to right.
+__device__ __forceinline__ int subtree_leaves(const CollapseArgs& A, int node, int* out) {
+    int st[kMaxLeafTris + 1];
+    int sp = 0, nl = 0;
+    st[sp++] = node;
+    while (sp > 0) {
+        const int c = st[--sp];
+        if (c >= A.n - 1) { if (nl < kMaxLeafTris) out[nl] = c - (A.n - 1); ++nl; continue; }
+        const int2 cc = A.children[c];
+        st[sp++] = cc.y;
+        st[sp++] = cc.x;
+    }
+    return nl;
 }
 
 __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_in, int count_in,
@@ -423,9 +543,10 @@ __global__ void k_collapse_level(CollapseArgs A, const int2* __restrict__ items_
         int node_c = ch[k];
         int cnt = subtree_count(A, node_c);
         if ((leafbits >> k) & 1u) {
-            int first = node_c >= n - 1 ? node_c - (n - 1) : A.range[node_c].x;
+            int leaf_pos[kMaxLeafTris];
+            subtree_leaves(A, node_c, leaf_pos);
             for (int j = 0; j < cnt; ++j) {
-                uint32_t tri = A.vals[first + j];
+                uint32_t tri = A.vals[leaf_pos[j]];
                 const float* tp = reinterpret_cast<const float*>(A.tris + tri);
                 float v0x = tp[0], v0y = tp[1], v0z = tp[2];
                 float4* rec = A.tri_records + (size_t)(tri_base + tri_off + j) * kTriWords;
@@ -488,14 +609,19 @@ void free_bvh8(Bvh8& b) {
     b = Bvh8();
 }
 
-int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv,
+int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv, int builder,
                Bvh8* out, char* err, size_t err_len) {
     Bvh8 B;
     float4 *tlo = nullptr, *thi = nullptr, *blo = nullptr, *bhi = nullptr;
     uint32_t *bounds = nullptr, *vals = nullptr, *vals_s = nullptr, *counters = nullptr;
     uint64_t *keys = nullptr, *keys_s = nullptr;
-    int2 *children = nullptr, *range = nullptr, *items[2] = {nullptr, nullptr};
-    int *parent = nullptr, *flags = nullptr;
+    int2 *children = nullptr, *items[2] = {nullptr, nullptr};
+    int *parent = nullptr, *flags = nullptr, *count = nullptr;
+    int *clusters[2] = {nullptr, nullptr}, *nearest = nullptr, *ploc_counters = nullptr;
+    unsigned long long *pflags = nullptr, *pscan = nullptr;
+    void* scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    int ploc_rounds = 0;
     float* cost = nullptr;
     uint32_t* dec = nullptr;
     void* cub_tmp = nullptr;
@@ -522,7 +648,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     DSRT_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)n));
     DSRT_CUDA(cudaMalloc(&vals_s, sizeof(uint32_t) * (size_t)n));
     DSRT_CUDA(cudaMalloc(&children, sizeof(int2) * (size_t)n));
-    DSRT_CUDA(cudaMalloc(&range, sizeof(int2) * (size_t)n));
+    DSRT_CUDA(cudaMalloc(&count, sizeof(int) * (size_t)(2 * n)));
     DSRT_CUDA(cudaMalloc(&parent, sizeof(int) * (size_t)(2 * n)));
     DSRT_CUDA(cudaMalloc(&flags, sizeof(int) * (size_t)n));
     DSRT_CUDA(cudaMalloc(&blo, sizeof(float4) * (size_t)(2 * n)));
@@ -543,8 +669,40 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     DSRT_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_s, vals, vals_s, n, 0, 63, stream));
 
     DSRT_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
-    if (n > 1) k_hierarchy<<<(n - 1 + TB - 1) / TB, TB, 0, stream>>>(keys_s, n, children, parent, range);
-    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, range, blo, bhi, flags, cost, dec);
+    if (n > 1 && builder == DSRT_BUILDER_LBVH) {
+        k_hierarchy<<<(n - 1 + TB - 1) / TB, TB, 0, stream>>>(keys_s, n, children, parent);
+    } else if (n > 1) {
+        DSRT_CUDA(cudaMalloc(&clusters[0], sizeof(int) * (size_t)n));
+        DSRT_CUDA(cudaMalloc(&clusters[1], sizeof(int) * (size_t)n));
+        DSRT_CUDA(cudaMalloc(&nearest, sizeof(int) * (size_t)n));
+        DSRT_CUDA(cudaMalloc(&pflags, sizeof(unsigned long long) * (size_t)n));
+        DSRT_CUDA(cudaMalloc(&pscan, sizeof(unsigned long long) * (size_t)n));
+        DSRT_CUDA(cudaMalloc(&ploc_counters, sizeof(int) * 2));
+        DSRT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, pflags, pscan, n, stream));
+        DSRT_CUDA(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16));
+        k_ploc_leaves<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, blo, bhi, clusters[0]);
+        int m = n, next_id = n - 2, cur = 0;
+        while (m > 1) {
+            const int mb = (m + kPlocThreads - 1) / kPlocThreads;
+            k_ploc_nearest<<<mb, kPlocThreads, 0, stream>>>(clusters[cur], m, blo, bhi, nearest);
+            k_ploc_mark<<<mb, kPlocThreads, 0, stream>>>(nearest, m, pflags);
+            DSRT_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, pflags, pscan, m, stream));
+            k_ploc_merge<<<mb, kPlocThreads, 0, stream>>>(clusters[cur], nearest, m, pflags, pscan, next_id, children, parent,
+                                                          blo, bhi, clusters[cur ^ 1], ploc_counters);
+            DSRT_CUDA(cudaGetLastError());
+            int hc2[2];
+            DSRT_CUDA(cudaMemcpyAsync(hc2, ploc_counters, sizeof(hc2), cudaMemcpyDeviceToHost, stream));
+            DSRT_CUDA(cudaStreamSynchronize(stream));
+            if (hc2[0] >= m) { snprintf(err, err_len, "PLOC made no progress at %d clusters", m); goto fail; }
+            m = hc2[0];
+            next_id = hc2[1];
+            cur ^= 1;
+            ++ploc_rounds;
+        }
+        if (next_id != -1) { snprintf(err, err_len, "PLOC created %d inner nodes for %d triangles", n - 2 - next_id, n); goto fail; }
+        DSRT_CUDA(cudaMemsetAsync(parent, 0xFF, sizeof(int), stream));       // the root (node 0) has parent -1
+    }
+    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, count, blo, bhi, flags, cost, dec);
     DSRT_CUDA(cudaGetLastError());
 
     DSRT_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, stream));
@@ -569,7 +727,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
         }
         if (!(ext > 0.f)) ext = 1.f;
         CollapseArgs A;
-        A.n = n; A.children = children; A.range = range; A.blo = blo; A.bhi = bhi;
+        A.n = n; A.children = children; A.count = count; A.blo = blo; A.bhi = bhi;
         A.dec = dec; A.vals = vals_s; A.tris = d_tris; A.nodes = B.nodes; A.tri_records = B.tri_records;
         A.counters = counters;
         A.eps = ext * (1.0f / 524288.0f);         // 2^-19 of the scene size
@@ -603,6 +761,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
         B.num_nodes = (int)hc[0];
         B.num_tris = n;
         B.num_levels = levels;
+        B.build_rounds = ploc_rounds;
         memcpy(&B.sah_cost, &hc[3], 4);
         if ((int)hc[1] != n) {
             snprintf(err, err_len, "collapse emitted %u triangle records for %d triangles", hc[1], n);
@@ -615,7 +774,9 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     DSRT_CUDA(cudaEventElapsedTime(&B.build_ms, ev0, ev1));
 
     cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
-    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
+    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(count); cudaFree(parent);
+    cudaFree(clusters[0]); cudaFree(clusters[1]); cudaFree(nearest); cudaFree(pflags); cudaFree(pscan);
+    cudaFree(ploc_counters); cudaFree(scan_tmp);
     cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters); cudaFree(cost); cudaFree(dec);
     cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
@@ -624,7 +785,9 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
 
 fail:
     cudaFree(tlo); cudaFree(thi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_s);
-    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(range); cudaFree(parent);
+    cudaFree(vals); cudaFree(vals_s); cudaFree(children); cudaFree(count); cudaFree(parent);
+    cudaFree(clusters[0]); cudaFree(clusters[1]); cudaFree(nearest); cudaFree(pflags); cudaFree(pscan);
+    cudaFree(ploc_counters); cudaFree(scan_tmp);
     cudaFree(flags); cudaFree(blo); cudaFree(bhi); cudaFree(counters); cudaFree(cost); cudaFree(dec);
     cudaFree(items[0]); cudaFree(items[1]); cudaFree(cub_tmp);
     if (ev0) cudaEventDestroy(ev0);

@@ -17,6 +17,7 @@ struct Bvh8 {
     int num_nodes = 0;
     int num_tris = 0;
     int num_levels = 0;
+    int build_rounds = 0;            // PLOC merge rounds (0 for the radix tree)
     float build_ms = 0.f;
     float sah_cost = 0.f;
     float scene_lo[3] = {0, 0, 0};
@@ -25,7 +26,8 @@ struct Bvh8 {
 
 // Builds the wide BVH for `n` triangles already resident on the device in the reference's
 // 116-byte layout.  Returns 0, or -1 with a message in `err`.
-int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv,
+enum { DSRT_BUILDER_PLOC = 0, DSRT_BUILDER_LBVH = 1 };
+int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want_uv, int builder,
                Bvh8* out, char* err, size_t err_len);
 void free_bvh8(Bvh8& b);
 

@@ -218,7 +218,7 @@ def test_full_size_properties_1m_triangles(dsrt, poses):
     cam_pos, sun, cam = pose_cam(dsrt, poses, 0, 1920, 1080, 4, 10)
     with dsrt.Context(0) as c:
         st = c.upload_scene(tris, mats)
-        assert st.num_triangles == 1000000 and 100000 < st.num_wide_nodes < 500002
+        assert st.num_triangles == 1000000 and 50000 < st.num_wide_nodes < 500002
         params = dsrt.make_params(1920, 1080, 4, 10)
         fs = c.render(cam, sun, params)
         a = c.readback_accum()
