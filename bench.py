@@ -45,7 +45,8 @@ POSE_FILE = ROOT / "tests" / "golden" / "rendezvous_1s_dt0_01s.txt"
 
 def algorithmic_bytes_per_ray(ntris: int) -> float:
     """ray in (32 B) + hit out (16 B) + one root-to-leaf path through an 8-wide
-    BVH of 80-byte nodes + a 4-triangle leaf of 48-byte records."""
+    BVH of 80-byte nodes + a 4-triangle leaf of 48-byte records.  (The contract figure is fixed by the
+    survey; the nodes this library builds are 96 bytes, csrc/bvh8.cuh.)"""
     levels = max(1, math.ceil(math.log(max(ntris, 8) / 4.0, 8)))
     return 48.0 + 80.0 * levels + 4 * 48.0
 
@@ -216,7 +217,8 @@ def run_dsrt(a, rank, world, local_rank):
     poses = d.read_pose_file(POSE_FILE)
     tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
     ctx = d.Context(local_rank)
-    st = ctx.upload_scene(tris, mats)
+    st_first = ctx.upload_scene(tris, mats)       # includes one-off module loading and allocator warm-up
+    st = ctx.upload_scene(tris, mats)             # the same upload + GPU BVH build again: the repeatable cost
     ctx.set_stage_timing(True)
     if a.spb > 0:
         ctx.set_samples_per_batch(a.spb)
@@ -329,7 +331,8 @@ def run_dsrt(a, rank, world, local_rank):
                        "rng": "philox4x32-10", "l2": "flushed between steps (256 MiB write)",
                        "frames_per_s": world * a.steps / (ms * 1e-3) if a.mode == "frame" else a.steps / (ms * 1e-3),
                        "bvh": {"wide_nodes": st.num_wide_nodes, "levels": st.num_levels, "build_ms": st.build_ms,
-                               "upload_ms": st.upload_ms, "sah": st.sah_cost}},
+                               "build_ms_first_call": st_first.build_ms, "upload_ms": st.upload_ms, "sah": st.sah_cost,
+                               "builder": os.environ.get("DSRT_BVH_BUILDER", "ploc")}},
             "clocks": clk,
             "e2e": {"value": (e2e_rays / (e2e_ms * 1e3)) if e2e_ms else None, "unit": "Mrays/s",
                     "h2d_bytes_per_step": 104 + 48 + 24 + 8, "d2h_bytes_per_step": a.width * a.height * 3,

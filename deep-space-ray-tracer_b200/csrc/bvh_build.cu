@@ -31,6 +31,7 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "bvh8.cuh"
 
@@ -180,7 +181,8 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n,
 // Ties in the merged area are broken towards the lower position, which guarantees that the
 // globally cheapest pair is mutual (so every round merges at least one pair) and makes the tree,
 // and with it every frame, reproducible from run to run.
-constexpr int kPlocRadius = 16;
+constexpr int kPlocRadius = 16;          // default search radius
+constexpr int kPlocMaxRadius = 64;
 
 __device__ __forceinline__ float union_half_area(float4 l0, float4 h0, float4 l1, float4 h1) {
     const float dx = fmaxf(h0.x, h1.x) - fminf(l0.x, l1.x);
@@ -203,13 +205,13 @@ __global__ void k_ploc_leaves(const uint32_t* __restrict__ vals, const float4* _
 constexpr int kPlocThreads = 256;
 __global__ void __launch_bounds__(kPlocThreads)
 k_ploc_nearest(const int* __restrict__ clusters, int m, const float4* __restrict__ blo,
-               const float4* __restrict__ bhi, int* __restrict__ nearest) {
+               const float4* __restrict__ bhi, int* __restrict__ nearest, int radius) {
     // the boxes of this block's window [base - R, base + T + R) staged in shared memory
-    __shared__ float4 s_lo[kPlocThreads + 2 * kPlocRadius];
-    __shared__ float4 s_hi[kPlocThreads + 2 * kPlocRadius];
+    __shared__ float4 s_lo[kPlocThreads + 2 * kPlocMaxRadius];
+    __shared__ float4 s_hi[kPlocThreads + 2 * kPlocMaxRadius];
     const int base = blockIdx.x * kPlocThreads;
-    for (int t = threadIdx.x; t < kPlocThreads + 2 * kPlocRadius; t += kPlocThreads) {
-        const int j = base - kPlocRadius + t;
+    for (int t = threadIdx.x; t < kPlocThreads + 2 * radius; t += kPlocThreads) {
+        const int j = base - radius + t;
         if (j >= 0 && j < m) {
             const int c = clusters[j];
             s_lo[t] = __ldg(&blo[c]);
@@ -219,13 +221,13 @@ k_ploc_nearest(const int* __restrict__ clusters, int m, const float4* __restrict
     __syncthreads();
     const int i = base + threadIdx.x;
     if (i >= m) return;
-    const float4 l = s_lo[threadIdx.x + kPlocRadius], h = s_hi[threadIdx.x + kPlocRadius];
+    const float4 l = s_lo[threadIdx.x + radius], h = s_hi[threadIdx.x + radius];
     float best = FLT_MAX;
     int bj = -1;
-    const int j0 = max(0, i - kPlocRadius), j1 = min(m - 1, i + kPlocRadius);
+    const int j0 = max(0, i - radius), j1 = min(m - 1, i + radius);
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
-        const int t = j - base + kPlocRadius;
+        const int t = j - base + radius;
         const float a = union_half_area(l, h, s_lo[t], s_hi[t]);
         if (a < best) { best = a; bj = j; }        // ascending j and a strict test: lowest position wins ties
     }
@@ -285,7 +287,7 @@ __global__ void k_ploc_merge(const int* __restrict__ clusters, const int* __rest
 //   D(n,j)   = min over 0<k<j of C(left,k) + C(right,j-k)
 // dec packs 3 bits per i: i=1: 0 leaf / 1 wide node; i=2..7: 0 = "use i-1", else k; i=8: k.
 constexpr float kCostNode = 1.0f;
-constexpr float kCostPrim = 0.3f;
+constexpr float kCostPrimDefault = 0.3f;
 
 __device__ __forceinline__ float box_half_area(float4 l, float4 h) {
     float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
@@ -297,7 +299,7 @@ __global__ void k_refit(const uint32_t* __restrict__ vals, const float4* __restr
                         const int2* __restrict__ children, const int* __restrict__ parent,
                         int* __restrict__ count,
                         float4* __restrict__ blo, float4* __restrict__ bhi, int* __restrict__ flags,
-                        float* __restrict__ cost, uint32_t* __restrict__ dec) {
+                        float* __restrict__ cost, uint32_t* __restrict__ dec, float kCostPrim) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t tri = vals[k];
@@ -632,6 +634,8 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     uint32_t hb[12];
     uint32_t hc[4];
     int level_count = 1, levels = 0;
+    float cost_prim = kCostPrimDefault;
+    if (const char* e = getenv("DSRT_COST_PRIM")) cost_prim = (float)atof(e);       // tuning experiments only
     size_t max_nodes = 0;
 
     if (n <= 0) { *out = B; return 0; }
@@ -682,9 +686,11 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
         DSRT_CUDA(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16));
         k_ploc_leaves<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, blo, bhi, clusters[0]);
         int m = n, next_id = n - 2, cur = 0;
+        int radius = kPlocRadius;
+        if (const char* e = getenv("DSRT_PLOC_RADIUS")) radius = max(1, min(kPlocMaxRadius, atoi(e)));     // tuning experiments only
         while (m > 1) {
             const int mb = (m + kPlocThreads - 1) / kPlocThreads;
-            k_ploc_nearest<<<mb, kPlocThreads, 0, stream>>>(clusters[cur], m, blo, bhi, nearest);
+            k_ploc_nearest<<<mb, kPlocThreads, 0, stream>>>(clusters[cur], m, blo, bhi, nearest, radius);
             k_ploc_mark<<<mb, kPlocThreads, 0, stream>>>(nearest, m, pflags);
             DSRT_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, pflags, pscan, m, stream));
             k_ploc_merge<<<mb, kPlocThreads, 0, stream>>>(clusters[cur], nearest, m, pflags, pscan, next_id, children, parent,
@@ -702,7 +708,7 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
         if (next_id != -1) { snprintf(err, err_len, "PLOC created %d inner nodes for %d triangles", n - 2 - next_id, n); goto fail; }
         DSRT_CUDA(cudaMemsetAsync(parent, 0xFF, sizeof(int), stream));       // the root (node 0) has parent -1
     }
-    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, count, blo, bhi, flags, cost, dec);
+    k_refit<<<nb, TB, 0, stream>>>(vals_s, tlo, thi, n, children, parent, count, blo, bhi, flags, cost, dec, cost_prim);
     DSRT_CUDA(cudaGetLastError());
 
     DSRT_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, stream));

@@ -2,6 +2,9 @@
 
     python profiles/summarize_ncu.py launches gpurun_out/launches.csv  > profiles/rNN_launches.txt
     python profiles/summarize_ncu.py kernel   gpurun_out/prof.ncu-rep  > profiles/rNN_kernel.txt
+    python profiles/summarize_ncu.py traffic  gpurun_out/traffic.ncu-rep "<workload name>" > profiles/trace_ncu_summary.json
+        (a capture of every k_primary / k_trace / k_tail launch of `bench.py --steps 1 --warmup 1`: DRAM bytes
+         of the traversal launches of the LAST step, which bench.py reports as roofline.traffic)
 """
 import collections
 import csv
@@ -65,5 +68,46 @@ def kernel(path):
             print(f"{k:88s} {units[i]:16s} " + " | ".join(r[i] for r in data))
 
 
+def traffic(path, workload):
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {k: hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
+                                     "lts__t_bytes.sum")}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+
+    def val(r, k):
+        return float(r[col[k]].replace(",", "")) * scale.get(units[col[k]], 1.0)
+    steps, cur = [], None
+    for r in data:
+        name = r[col["Kernel Name"]]
+        short = "k_primary" if "k_primary" in name else "k_trace" if "k_trace" in name else "k_tail" if "k_tail" in name else None
+        if short is None:
+            continue
+        if short == "k_primary":
+            cur = []
+            steps.append(cur)
+        if cur is None:
+            continue
+        cur.append({"kernel": short, "dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum"),
+                    "l2_bytes": val(r, "lts__t_bytes.sum"), "ms": val(r, "gpu__time_duration.sum")})
+    last = steps[-1]
+    res = {"workload": workload, "source": path.split("/")[-1],
+           "note": "ncu --set full, default cache control (every launch starts with cold caches): an upper bound on the "
+                   "DRAM traffic of the same launches inside an un-profiled step",
+           "launches_in_step": len(last),
+           "dram_bytes_per_step": sum(x["dram_read"] + x["dram_write"] for x in last),
+           "dram_read_bytes_per_step": sum(x["dram_read"] for x in last),
+           "dram_write_bytes_per_step": sum(x["dram_write"] for x in last),
+           "l2_bytes_per_step": sum(x["l2_bytes"] for x in last),
+           "ncu_ms_per_step": sum(x["ms"] for x in last),
+           "per_launch": last}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])

@@ -16,3 +16,8 @@ $PROF > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:k_primary|k_trace|k_shade' -c 7 -f -o gpurun_out/prof_$TAG $PROF > gpurun_out/ncu2_$TAG.log 2>&1
 echo ncu2_rc=$?
 tail -2 gpurun_out/ncu2_$TAG.log
+# DRAM traffic of the traversal launches of one step of the DEFAULT workload (bench.py's roofline.traffic)
+TR="python bench.py --steps 1 --warmup 1 --no_cpu_baseline --no_e2e --no_ref_gpu"
+$TR > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --set full --clock-control none -k 'regex:k_primary|k_trace|k_tail' -c 60 -f -o gpurun_out/traffic_$TAG $TR > gpurun_out/ncu3_$TAG.log 2>&1
+echo ncu3_rc=$?
