@@ -58,8 +58,8 @@ struct FrameConst {
     float4* hits;                     // t,u,v,bits(id) per queue entry; id = uploaded triangle index,
                                       // -1 = miss, -2 - i = sphere i
     float4* st_a;                     // per path: throughput.xyz, bits(rng state / draw index)
-    float4* st_b;                     // per path: L.xyz (clamped when finished), bits(depth)
-    float4* sq_o;                     // shadow queue: origin.xyz, bits(path | final<<31)
+    float4* st_b;                     // per path: L.xyz (k_resolve applies the per-sample clamp), unused
+    float4* sq_o;                     // shadow queue: origin.xyz, bits(path)
     float4* sq_l;                     // shadow queue: L if the sun is visible
     uint32_t* rng_pix;                // LCG replay: per-pixel generator state
     float* accum;                     // W*H*3 sum of clamped samples, row 0 = bottom
