@@ -95,6 +95,7 @@ SYMBOLS = [
     "dsrt_create", "dsrt_destroy", "dsrt_last_error", "dsrt_stream",
     "dsrt_scene_upload", "dsrt_scene_upload_device", "dsrt_scene_stats", "dsrt_scene_download",
     "dsrt_render_frame", "dsrt_frame_stats", "dsrt_set_stage_timing", "dsrt_set_samples_per_batch",
+    "dsrt_set_bvh_builder",
     "dsrt_readback_rgb8", "dsrt_readback_accum", "dsrt_accum_device", "dsrt_upload_accum",
     "dsrt_trace_closest", "dsrt_trace_occluded", "dsrt_first_hits",
     "dsrt_trace_closest_device", "dsrt_trace_occluded_device",
@@ -121,6 +122,7 @@ lib.dsrt_render_frame.argtypes = [_vp, C.POINTER(Camera), C.POINTER(_f), C.POINT
 lib.dsrt_frame_stats.argtypes = [_vp, C.POINTER(FrameStats)]
 lib.dsrt_set_stage_timing.argtypes = [_vp, _i]
 lib.dsrt_set_samples_per_batch.argtypes = [_vp, _i]
+lib.dsrt_set_bvh_builder.argtypes = [_vp, _i]
 lib.dsrt_readback_rgb8.argtypes = [_vp, _i, _f, _vp, C.c_size_t]
 lib.dsrt_readback_accum.argtypes = [_vp, _vp, C.c_size_t]
 lib.dsrt_accum_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
@@ -335,6 +337,10 @@ class Context:
 
     def set_samples_per_batch(self, n: int):
         self._ck(lib.dsrt_set_samples_per_batch(self._h, int(n)))
+
+    def set_bvh_builder(self, name: str):
+        """'ploc' (default) or 'lbvh': the binary-tree stage used by the next upload_scene."""
+        self._ck(lib.dsrt_set_bvh_builder(self._h, {"ploc": 0, "lbvh": 1}[name]))
 
     def readback_rgb8(self, total_spp: int, gamma: float = 2.0, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

@@ -378,6 +378,12 @@ extern "C" int dsrt_set_stage_timing(dsrt_ctx* ctx, int enabled) {
     return DSRT_OK;
 }
 
+extern "C" int dsrt_set_bvh_builder(dsrt_ctx* ctx, int builder) {
+    if (!ctx || (builder != DSRT_BUILDER_PLOC && builder != DSRT_BUILDER_LBVH)) return DSRT_EINVAL;
+    ctx->builder = builder;
+    return DSRT_OK;
+}
+
 extern "C" int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples) {
     if (!ctx || samples < 0) return DSRT_EINVAL;
     ctx->spb_override = samples;

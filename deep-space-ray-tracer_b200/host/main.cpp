@@ -15,6 +15,11 @@
 // when the file cannot be opened the deterministic synthetic station stands in (the NASA model
 // is not redistributable with either tree).
 //
+// Frame-parallel runs over several GPUs use one PROCESS per GPU (forked before the first CUDA call):
+// CUDA context creation costs ~2.5 s on a B200 box and is serialised inside a process, which would
+// otherwise dominate a 99-frame sequence on 8 GPUs.  Each worker owns its GPU, renders frames
+// k = g, g+G, ... and writes its own files; there is no collective.
+//
 // Frames are written by a writer thread per GPU (PPM, then the in-process PNG encoder that
 // replaces the reference's `magick` subprocess, main.cpp:28-36), so a GPU renders frame k+1
 // while frame k is being compressed.
@@ -38,6 +43,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <sys/wait.h>
+#include <unistd.h>
 
 #ifdef DSRT_WITH_NCCL
 #include <cuda_runtime.h>
@@ -434,11 +442,57 @@ int main(int argc, char** argv) {
 #endif
     } else {
         std::atomic<int> errors(0);
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; ++g)
-            th.emplace_back(frame_worker, g, std::cref(o), std::cref(scene), std::cref(jobs), g, G,
-                            std::ref(results), std::ref(errors), std::ref(times[(size_t)g]));
-        for (auto& t : th) t.join();
+        if (G == 1) {
+            frame_worker(0, o, scene, jobs, 0, 1, results, errors, times[0]);
+        } else {
+            // one worker process per GPU; results come back through a pipe
+            struct Wire { size_t k; FrameResult r; };
+            std::cout.flush();
+            std::fflush(stdout);
+            std::vector<pid_t> pids((size_t)G, -1);
+            std::vector<int> rfd((size_t)G, -1);
+            for (int g = 0; g < G; ++g) {
+                int fd[2];
+                if (pipe(fd) != 0) { std::perror("pipe"); return 1; }
+                const pid_t pid = fork();
+                if (pid < 0) { std::perror("fork"); return 1; }
+                if (pid == 0) {
+                    close(fd[0]);
+                    for (int q = 0; q < g; ++q) close(rfd[(size_t)q]);
+                    frame_worker(g, o, scene, jobs, g, G, results, errors, times[(size_t)g]);
+                    std::cout.flush();
+                    bool ok = write(fd[1], &times[(size_t)g], sizeof(SetupTimes)) == (ssize_t)sizeof(SetupTimes);
+                    for (size_t k = (size_t)g; k < jobs.size() && ok; k += (size_t)G) {
+                        const Wire w{k, results[k]};
+                        ok = write(fd[1], &w, sizeof(w)) == (ssize_t)sizeof(w);
+                    }
+                    close(fd[1]);
+                    _exit((errors || !ok) ? 1 : 0);
+                }
+                close(fd[1]);
+                pids[(size_t)g] = pid;
+                rfd[(size_t)g] = fd[0];
+            }
+            for (int g = 0; g < G; ++g) {
+                auto read_all = [&](void* dst, size_t n) {
+                    size_t got = 0;
+                    while (got < n) {
+                        const ssize_t r = read(rfd[(size_t)g], (char*)dst + got, n - got);
+                        if (r <= 0) return false;
+                        got += (size_t)r;
+                    }
+                    return true;
+                };
+                if (!read_all(&times[(size_t)g], sizeof(SetupTimes))) ++errors;
+                Wire w;
+                while (read_all(&w, sizeof(w)))
+                    if (w.k < results.size()) results[w.k] = w.r;
+                close(rfd[(size_t)g]);
+                int status = 0;
+                waitpid(pids[(size_t)g], &status, 0);
+                if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ++errors;
+            }
+        }
         rc = errors ? 1 : 0;
     }
 

@@ -101,6 +101,13 @@ int dsrt_set_stage_timing(dsrt_ctx* ctx, int enabled);
 /* Samples of a pixel that are in flight together in Philox mode (0 = choose from the image
  * size).  The LCG replay always uses 1. */
 int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples);
+/* Binary-tree stage of the GPU BVH build used by the NEXT dsrt_scene_upload: 0 = PLOC (parallel
+ * locally-ordered clustering, the default: lowest SAH cost), 1 = binary radix tree over the Morton
+ * order (fastest build).  Both feed the same SAH-optimal collapse into the 8-wide BVH, and both
+ * replace build_bvh_recursive (/root/reference/src/gpu_scene_builder.cpp:343-442). */
+#define DSRT_BVH_PLOC 0
+#define DSRT_BVH_LBVH 1
+int dsrt_set_bvh_builder(dsrt_ctx* ctx, int builder);
 
 /* Tone-map the accumulation buffer exactly as the reference kernel's tail
  * (gpu_render.cu:1003-1030: mean over total_spp, max 0, min 10, powf(c, 1/gamma), clamp,

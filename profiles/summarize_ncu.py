@@ -74,7 +74,7 @@ def traffic(path, workload):
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {k: hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
-                                     "lts__t_bytes.sum")}
+                                     "l1tex__m_xbar2l1tex_read_bytes.sum")}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
     def val(r, k):
@@ -91,7 +91,7 @@ def traffic(path, workload):
         if cur is None:
             continue
         cur.append({"kernel": short, "dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum"),
-                    "l2_bytes": val(r, "lts__t_bytes.sum"), "ms": val(r, "gpu__time_duration.sum")})
+                    "l2_to_sm_read_bytes": val(r, "l1tex__m_xbar2l1tex_read_bytes.sum"), "ms": val(r, "gpu__time_duration.sum")})
     last = steps[-1]
     res = {"workload": workload, "source": path.split("/")[-1],
            "note": "ncu --set full, default cache control (every launch starts with cold caches): an upper bound on the "
@@ -100,7 +100,7 @@ def traffic(path, workload):
            "dram_bytes_per_step": sum(x["dram_read"] + x["dram_write"] for x in last),
            "dram_read_bytes_per_step": sum(x["dram_read"] for x in last),
            "dram_write_bytes_per_step": sum(x["dram_write"] for x in last),
-           "l2_bytes_per_step": sum(x["l2_bytes"] for x in last),
+           "l2_to_sm_read_bytes_per_step": sum(x["l2_to_sm_read_bytes"] for x in last),
            "ncu_ms_per_step": sum(x["ms"] for x in last),
            "per_launch": last}
     print(json.dumps(res, indent=1))

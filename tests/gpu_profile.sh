@@ -10,7 +10,7 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo 
 cat gpurun_out/bench_$TAG.json
 PROF="python bench.py --steps 1 --warmup 1 --spp 16 --no_cpu_baseline --no_e2e"
 $PROF > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $PROF > gpurun_out/ncu1_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv $PROF > gpurun_out/ncu1_$TAG.log 2>&1
 echo ncu1_rc=$?
 $PROF > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:k_primary|k_trace|k_shade' -c 7 -f -o gpurun_out/prof_$TAG $PROF > gpurun_out/ncu2_$TAG.log 2>&1

@@ -48,6 +48,22 @@ def test_bvh_invariants(ctx, mesh10k):
     assert s.num_triangles == 10000 and s.num_wide_nodes == len(nodes) and s.max_leaf_tris == 3
 
 
+def test_both_builders_same_hits(dsrt, mesh10k, oracle_scene10k):
+    """The radix-tree builder (DSRT_BVH_LBVH) and PLOC (default) give different trees over the same
+    triangles; the hits must not depend on the tree (bit-exact against the oracle for both)."""
+    tris, mats = mesh10k
+    rays = random_rays(20000, 7, np.array([-950, -420, -25.0]), np.array([950, 420, 25.0]))
+    ref = oracle_scene10k.trace(rays)
+    stats = {}
+    with dsrt.Context(0) as c:
+        for name in ("lbvh", "ploc"):
+            c.set_bvh_builder(name)
+            stats[name] = c.upload_scene(tris, mats)
+            check_bvh(*c.download_bvh(), tris)
+            assert_hits_equal(c.trace_closest(rays), ref, 0)
+    assert stats["ploc"].sah_cost < stats["lbvh"].sah_cost          # why PLOC is the default
+
+
 @pytest.mark.parametrize("frame", [0, 49, 98])
 def test_first_hits_bit_exact_vs_oracle(dsrt, poses, ctx, oracle_scene10k, frame):
     _, _, cam = pose_cam(dsrt, poses, frame)
