@@ -18,8 +18,10 @@ sun with shadow rays.  Metric: Mrays/s (primary + bounce + shadow rays traced / 
   cpu_baseline  the reference's CPU camera/bvh_node path (oracle/_ref/libref_cpu.so) on the
              host cores, on a bounded sample of the same frame (rank 0, N = 1 only)
 
-N > 1: frame-parallel -- rank r renders pose (step*N + r) of the sequence, no collective
-(scaling "weak": per-GPU work fixed).  --mode sample shards ONE frame's samples over the
+N > 1: frame-parallel -- every rank renders its own frame of the same configuration (pose 0) per
+step, no collective (scaling "weak": per-GPU work fixed, N frames per step).  --poses sequence
+walks the pose file instead (rank r renders pose step*N + r; later poses are closer to the station
+and cost more, so steps are then not comparable across N).  --mode sample shards ONE frame's samples over the
 ranks and sums the float accumulation buffers with one NCCL reduce ("strong").
 """
 from __future__ import annotations
@@ -128,6 +130,8 @@ def parse_args():
                     help="BASELINE.json presets: c2 = the default; c4 = 3840x2160, 1000 spp (use with --mode sample); "
                          "c5 = 10M triangles, diffuse only, depth 16, 1080p, 256 spp")
     ap.add_argument("--no_ref_gpu", action="store_true", help="skip timing the reference's own GPU kernel beside the result")
+    ap.add_argument("--poses", default="fixed", choices=["fixed", "sequence"],
+                    help="frame-parallel runs: every rank renders pose 0 (fixed, the default) or rank r renders pose step*N + r")
     a = ap.parse_args()
     if a.config == "c4":
         a.width, a.height, a.spp = 3840, 2160, 1000
@@ -229,7 +233,9 @@ def run_dsrt(a, rank, world, local_rank):
 
     def frame_inputs(i):
         # frame-parallel: step i covers frames i*world .. i*world+world-1, rank r takes its own
-        idx = (sharding.frames_of_rank((i + 1) * world, rank, world)[i]) % len(poses) if (world > 1 and a.mode == "frame") else 0
+        idx = 0
+        if world > 1 and a.mode == "frame" and a.poses == "sequence":
+            idx = (sharding.frames_of_rank((i + 1) * world, rank, world)[i]) % len(poses)
         cam_pos, sun, _ = d.pose_to_model_frame(poses[idx])
         return d.camera_look_at_origin(cam_pos, 40.0, a.width, a.height, a.spp, a.depth), sun
 

@@ -15,9 +15,10 @@
 // when the file cannot be opened the deterministic synthetic station stands in (the NASA model
 // is not redistributable with either tree).
 //
-// Frame-parallel runs over several GPUs use one PROCESS per GPU (forked before the first CUDA call):
-// CUDA context creation costs ~2.5 s on a B200 box and is serialised inside a process, which would
-// otherwise dominate a 99-frame sequence on 8 GPUs.  Each worker owns its GPU, renders frames
+// Runs over several GPUs use one PROCESS per GPU (forked before the first CUDA call), the same
+// model as `torchrun bench.py`.  CUDA start-up costs ~2.4 s per process on a B200 box (measured;
+// it is paid before the first kernel and is outside this library's control) and is reported
+// separately from the frame loop in --stats_json.  Each worker owns its GPU, renders frames
 // k = g, g+G, ... and writes its own files; there is no collective.
 //
 // Frames are written by a writer thread per GPU (PPM, then the in-process PNG encoder that
@@ -213,13 +214,13 @@ private:
 };
 
 // One GPU renders the frames jobs[k] with k % stride == offset.
-void frame_worker(int device, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
+void frame_worker(int device, int label, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
                   int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors, SetupTimes& times) {
     dsrt_ctx* ctx = nullptr;
     auto t0 = std::chrono::high_resolution_clock::now();
     if (dsrt_create(&ctx, device) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
-        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(nullptr));
+        std::fprintf(stderr, "GPU %d: %s\n", label, dsrt_last_error(nullptr));
         ++errors;
         return;
     }
@@ -227,7 +228,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
     t0 = std::chrono::high_resolution_clock::now();
     if (upload(ctx, scene) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
-        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(ctx));
+        std::fprintf(stderr, "GPU %d: %s\n", label, dsrt_last_error(ctx));
         ++errors;
         dsrt_destroy(ctx);
         return;
@@ -237,7 +238,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
         DsrtSceneStats st;
         dsrt_scene_stats(ctx, &st);
         std::lock_guard<std::mutex> l(g_print);
-        std::cout << "GPU " << device << " scene build time: " << st.build_ms << " ms (" << st.num_wide_nodes
+        std::cout << "GPU " << label << " scene build time: " << st.build_ms << " ms (" << st.num_wide_nodes
                   << " wide nodes, upload " << st.upload_ms << " ms)\n";
     }
     const DsrtRenderParams params = make_params(o);
@@ -253,7 +254,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
         if (k == (size_t)offset) times.first_frame_s = seconds_since(t0);
         if (rc != DSRT_OK) {
             std::lock_guard<std::mutex> l(g_print);
-            std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, device, dsrt_last_error(ctx));
+            std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, label, dsrt_last_error(ctx));
             ++errors;
             continue;                       // no stale file is renamed into place
         }
@@ -265,7 +266,7 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
         std::lock_guard<std::mutex> l(g_print);
         char name[64];
         std::snprintf(name, sizeof(name), "frame_%04zu.png", j.index);
-        std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << device << ", " << fs.device_ms << " ms, "
+        std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << label << ", " << fs.device_ms << " ms, "
                   << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
     }
     writer.finish();
@@ -275,73 +276,174 @@ void frame_worker(int device, const Options& o, const SceneData& scene, const st
     times.teardown_s = seconds_since(t0);
 }
 
+// Gives a forked worker process its own GPU: with `isolate` it sees only that device (so the CUDA
+// runtime initialises one device instead of all of them) and uses ordinal 0, otherwise it uses
+// ordinal g.  Returns the ordinal to pass to dsrt_create.
+int claim_gpu(int g, bool isolate) {
+    if (!isolate) return g;
+    std::string pick = std::to_string(g);
+    if (const char* vis = std::getenv("CUDA_VISIBLE_DEVICES")) {
+        std::vector<std::string> tok;
+        std::string cur;
+        for (const char* c = vis;; ++c) {
+            if (*c == ',' || *c == 0) { tok.push_back(cur); cur.clear(); if (*c == 0) break; }
+            else cur.push_back(*c);
+        }
+        if ((size_t)g < tok.size() && !tok[(size_t)g].empty()) pick = tok[(size_t)g];
+    }
+    setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+    return 0;
+}
+
+bool write_all(int fd, const void* src, size_t n) {
+    size_t put = 0;
+    while (put < n) {
+        const ssize_t r = write(fd, (const char*)src + put, n - put);
+        if (r <= 0) return false;
+        put += (size_t)r;
+    }
+    return true;
+}
+bool read_all(int fd, void* dst, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = read(fd, (char*)dst + got, n - got);
+        if (r <= 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
+
+struct Wire { size_t k; FrameResult r; };
+
 #ifdef DSRT_WITH_NCCL
-// One frame at a time, its samples split over the GPUs; one ncclReduce(sum) of the float
-// accumulation buffer to GPU 0, which tone-maps and writes the frame.
-int sample_sharded(const Options& o, const SceneData& scene,
-                   const std::vector<FrameJob>& jobs, std::vector<FrameResult>& results) {
-    const int G = o.gpus;
-    std::vector<dsrt_ctx*> ctx(G, nullptr);
-    std::vector<ncclComm_t> comm(G);
-    std::vector<int> devs(G);
-    for (int g = 0; g < G; ++g) devs[g] = g;
-    if (ncclCommInitAll(comm.data(), G, devs.data()) != ncclSuccess) { std::fprintf(stderr, "ncclCommInitAll failed\n"); return 1; }
+// One frame at a time, its samples split over the GPUs -- one worker process per GPU (as in the
+// frame-parallel mode, and for the same reason).  Worker g renders the global sample indices
+// [spp*g/G, spp*(g+1)/G) of every pixel; one ncclReduce(sum) of the float accumulation buffer over
+// NVLink brings the frame to worker 0, which tone-maps and writes it.  The NCCL id is created by
+// worker 0 and relayed by the parent, which itself never touches CUDA.
+int sample_worker(int g, int G, int id_fd, int out_fd, const Options& o, const SceneData& scene,
+                  const std::vector<FrameJob>& jobs, bool isolate) {
+    const int device = claim_gpu(g, isolate);
+    SetupTimes times;
+    auto t0 = std::chrono::high_resolution_clock::now();
+    dsrt_ctx* ctx = nullptr;
+    if (dsrt_create(&ctx, device) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(nullptr)); return 1; }
+    times.create_s = seconds_since(t0);
+    ncclUniqueId id;
+    if (g == 0) {
+        if (ncclGetUniqueId(&id) != ncclSuccess || !write_all(out_fd, &id, sizeof(id))) { std::fprintf(stderr, "ncclGetUniqueId failed\n"); return 1; }
+    }
+    if (!read_all(id_fd, &id, sizeof(id))) { std::fprintf(stderr, "GPU %d: no NCCL id\n", g); return 1; }
+    t0 = std::chrono::high_resolution_clock::now();
+    if (upload(ctx, scene) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx)); return 1; }
+    ncclComm_t comm;
+    cudaSetDevice(device);
+    if (ncclCommInitRank(&comm, G, id, g) != ncclSuccess) { std::fprintf(stderr, "GPU %d: ncclCommInitRank failed\n", g); return 1; }
+    times.upload_s = seconds_since(t0);
+
+    const DsrtRenderParams params = make_params(o);
+    std::vector<FrameResult> results(jobs.size());
     int errors = 0;
     {
-        std::vector<std::thread> th;
-        std::atomic<int> err(0);
-        for (int g = 0; g < G; ++g)
-            th.emplace_back([&, g] {
-                if (dsrt_create(&ctx[g], g) != DSRT_OK || upload(ctx[g], scene) != DSRT_OK) {
-                    std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx[g]));
-                    ++err;
-                }
-            });
-        for (auto& t : th) t.join();
-        errors = err;
-    }
-    if (errors) return 1;
-    const DsrtRenderParams params = make_params(o);
-    FrameWriter writer(o, results);
-    for (size_t k = 0; k < jobs.size(); ++k) {
-        const FrameJob& j = jobs[k];
-        std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
-        DsrtCamera cam;
-        dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
-        std::vector<std::thread> th;
-        std::atomic<int> err(0);
-        std::vector<double> ms(G, 0.0), rays(G, 0.0);
-        for (int g = 0; g < G; ++g)
-            th.emplace_back([&, g] {
-                // global sample indices stay global: the jitter depends on s/spp (gpu_render.cu:995-996)
-                const int s0 = (int)((long long)o.spp * g / G), s1 = (int)((long long)o.spp * (g + 1) / G);
-                if (dsrt_render_frame(ctx[g], &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, s0, s1, nullptr, 0) != DSRT_OK) { ++err; return; }
-                DsrtFrameStats fs;
-                dsrt_frame_stats(ctx[g], &fs);
-                ms[g] = fs.device_ms;
-                rays[g] = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
-            });
-        for (auto& t : th) t.join();
-        if (err) { std::fprintf(stderr, "frame %zu: render failed\n", j.index); ++errors; continue; }
-        ncclGroupStart();
-        for (int g = 0; g < G; ++g) {
+        FrameWriter writer(o, results);
+        t0 = std::chrono::high_resolution_clock::now();
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const FrameJob& j = jobs[k];
+            DsrtCamera cam;
+            dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
+            // global sample indices stay global: the jitter depends on s/spp (gpu_render.cu:995-996)
+            const int s0 = (int)((long long)o.spp * g / G), s1 = (int)((long long)o.spp * (g + 1) / G);
+            const bool rendered = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, s0, s1, nullptr, 0) == DSRT_OK;
+            if (!rendered) { std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, g, dsrt_last_error(ctx)); ++errors; }
+            DsrtFrameStats fs{};
+            dsrt_frame_stats(ctx, &fs);
+            // every worker takes part in the reduce even after a failed render (a zero buffer), so the
+            // collective cannot dead-lock
             void* acc = nullptr; size_t nf = 0;
-            dsrt_accum_device(ctx[g], &acc, &nf);
-            cudaSetDevice(g);
-            ncclReduce(acc, acc, nf, ncclFloat, ncclSum, 0, comm[g], (cudaStream_t)dsrt_stream(ctx[g]));
+            if (dsrt_accum_device(ctx, &acc, &nf) != DSRT_OK) { ++errors; break; }
+            cudaStream_t st = (cudaStream_t)dsrt_stream(ctx);
+            if (ncclReduce(acc, acc, nf, ncclFloat, ncclSum, 0, comm, st) != ncclSuccess) { ++errors; break; }
+            cudaStreamSynchronize(st);
+            results[k].device_ms = rendered ? fs.device_ms : 0.0;
+            results[k].rays = rendered ? (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays) : 0.0;
+            if (g == 0) {
+                std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+                if (dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb.data(), rgb.size()) != DSRT_OK) { ++errors; continue; }
+                writer.push(k, j.index, std::move(rgb));
+                std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, GPU 0: " << fs.device_ms << " ms]\n";
+            } else {
+                results[k].done = rendered;
+            }
+            if (k == 0) times.first_frame_s = seconds_since(t0);
         }
-        ncclGroupEnd();
-        for (int g = 0; g < G; ++g) { cudaSetDevice(g); cudaStreamSynchronize((cudaStream_t)dsrt_stream(ctx[g])); }
-        if (dsrt_readback_rgb8(ctx[0], o.spp, params.gamma, rgb.data(), rgb.size()) != DSRT_OK) { ++errors; continue; }
-        double mx = 0, total = 0;
-        for (int g = 0; g < G; ++g) { mx = std::max(mx, ms[g]); total += rays[g]; }
-        results[k].device_ms = mx; results[k].rays = total;
-        writer.push(k, j.index, std::move(rgb));
-        std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, " << mx << " ms, "
-                  << total / (mx * 1e3) << " Mrays/s]\n";
+        writer.finish();
+        times.loop_s = seconds_since(t0);
     }
-    writer.finish();
-    for (int g = 0; g < G; ++g) { dsrt_destroy(ctx[g]); ncclCommDestroy(comm[g]); }
+    t0 = std::chrono::high_resolution_clock::now();
+    ncclCommDestroy(comm);
+    dsrt_destroy(ctx);
+    times.teardown_s = seconds_since(t0);
+    std::cout.flush();
+    bool ok = write_all(out_fd, &times, sizeof(times));
+    for (size_t k = 0; k < jobs.size() && ok; ++k) {
+        const Wire w{k, results[k]};
+        ok = write_all(out_fd, &w, sizeof(w));
+    }
+    return (errors || !ok) ? 1 : 0;
+}
+
+int sample_sharded(const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
+                   std::vector<FrameResult>& results, std::vector<SetupTimes>& times, bool isolate) {
+    const int G = o.gpus;
+    std::cout.flush();
+    std::fflush(stdout);
+    std::vector<pid_t> pids((size_t)G, -1);
+    std::vector<int> to_child((size_t)G, -1), from_child((size_t)G, -1);
+    for (int g = 0; g < G; ++g) {
+        int down[2], up[2];
+        if (pipe(down) != 0 || pipe(up) != 0) { std::perror("pipe"); return 1; }
+        const pid_t pid = fork();
+        if (pid < 0) { std::perror("fork"); return 1; }
+        if (pid == 0) {
+            close(down[1]); close(up[0]);
+            for (int q = 0; q < g; ++q) { close(to_child[(size_t)q]); close(from_child[(size_t)q]); }
+            const int rc = sample_worker(g, G, down[0], up[1], o, scene, jobs, isolate);
+            close(up[1]);
+            _exit(rc);
+        }
+        close(down[0]); close(up[1]);
+        pids[(size_t)g] = pid; to_child[(size_t)g] = down[1]; from_child[(size_t)g] = up[0];
+    }
+    int errors = 0;
+    ncclUniqueId id;
+    if (read_all(from_child[0], &id, sizeof(id))) {
+        for (int g = 0; g < G; ++g) if (!write_all(to_child[(size_t)g], &id, sizeof(id))) ++errors;
+    } else {
+        ++errors;
+    }
+    for (int g = 0; g < G; ++g) close(to_child[(size_t)g]);       // a worker waiting for an id that never comes sees EOF
+    std::vector<std::vector<FrameResult>> per((size_t)G, std::vector<FrameResult>(jobs.size()));
+    for (int g = 0; g < G; ++g) {
+        if (!read_all(from_child[(size_t)g], &times[(size_t)g], sizeof(SetupTimes))) ++errors;
+        Wire w;
+        while (read_all(from_child[(size_t)g], &w, sizeof(w)))
+            if (w.k < jobs.size()) per[(size_t)g][w.k] = w.r;
+        close(from_child[(size_t)g]);
+        int status = 0;
+        waitpid(pids[(size_t)g], &status, 0);
+        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ++errors;
+    }
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        bool done = true;
+        double mx = 0, total = 0;
+        for (int g = 0; g < G; ++g) {
+            done = done && per[(size_t)g][k].done;
+            mx = std::max(mx, per[(size_t)g][k].device_ms);
+            total += per[(size_t)g][k].rays;
+        }
+        results[k].done = done; results[k].device_ms = mx; results[k].rays = total;
+    }
     return errors ? 1 : 0;
 }
 #endif
@@ -432,10 +534,13 @@ int main(int argc, char** argv) {
     int rc = 0;
     const int G = std::max(1, o.gpus);
     std::vector<SetupTimes> times((size_t)G);
+    // DSRT_CLI_ISOLATE=1 hides the other GPUs from each worker process.  Off by default: measured on B200 boxes it
+    // does not shorten CUDA start-up (2.4 s vs 3.6 s per process at 2 GPUs) and slows NCCL's set-up.
+    const bool isolate = std::getenv("DSRT_CLI_ISOLATE") && std::atoi(std::getenv("DSRT_CLI_ISOLATE")) != 0;
     const auto render_start = clk::now();
     if (o.shard == "sample" && G > 1) {
 #ifdef DSRT_WITH_NCCL
-        rc = sample_sharded(o, scene, jobs, results);
+        rc = sample_sharded(o, scene, jobs, results, times, isolate);
 #else
         std::fprintf(stderr, "--shard sample needs a build with NCCL\n");
         rc = 1;
@@ -443,10 +548,9 @@ int main(int argc, char** argv) {
     } else {
         std::atomic<int> errors(0);
         if (G == 1) {
-            frame_worker(0, o, scene, jobs, 0, 1, results, errors, times[0]);
+            frame_worker(0, 0, o, scene, jobs, 0, 1, results, errors, times[0]);
         } else {
             // one worker process per GPU; results come back through a pipe
-            struct Wire { size_t k; FrameResult r; };
             std::cout.flush();
             std::fflush(stdout);
             std::vector<pid_t> pids((size_t)G, -1);
@@ -459,12 +563,13 @@ int main(int argc, char** argv) {
                 if (pid == 0) {
                     close(fd[0]);
                     for (int q = 0; q < g; ++q) close(rfd[(size_t)q]);
-                    frame_worker(g, o, scene, jobs, g, G, results, errors, times[(size_t)g]);
+                    const int device = claim_gpu(g, isolate);
+                    frame_worker(device, g, o, scene, jobs, g, G, results, errors, times[(size_t)g]);
                     std::cout.flush();
-                    bool ok = write(fd[1], &times[(size_t)g], sizeof(SetupTimes)) == (ssize_t)sizeof(SetupTimes);
+                    bool ok = write_all(fd[1], &times[(size_t)g], sizeof(SetupTimes));
                     for (size_t k = (size_t)g; k < jobs.size() && ok; k += (size_t)G) {
                         const Wire w{k, results[k]};
-                        ok = write(fd[1], &w, sizeof(w)) == (ssize_t)sizeof(w);
+                        ok = write_all(fd[1], &w, sizeof(w));
                     }
                     close(fd[1]);
                     _exit((errors || !ok) ? 1 : 0);
@@ -474,18 +579,9 @@ int main(int argc, char** argv) {
                 rfd[(size_t)g] = fd[0];
             }
             for (int g = 0; g < G; ++g) {
-                auto read_all = [&](void* dst, size_t n) {
-                    size_t got = 0;
-                    while (got < n) {
-                        const ssize_t r = read(rfd[(size_t)g], (char*)dst + got, n - got);
-                        if (r <= 0) return false;
-                        got += (size_t)r;
-                    }
-                    return true;
-                };
-                if (!read_all(&times[(size_t)g], sizeof(SetupTimes))) ++errors;
+                if (!read_all(rfd[(size_t)g], &times[(size_t)g], sizeof(SetupTimes))) ++errors;
                 Wire w;
-                while (read_all(&w, sizeof(w)))
+                while (read_all(rfd[(size_t)g], &w, sizeof(w)))
                     if (w.k < results.size()) results[w.k] = w.r;
                 close(rfd[(size_t)g]);
                 int status = 0;
