@@ -418,6 +418,40 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
     fc.num_sphere_lights = ctx->nsphere_lights;
 }
 
+// Pixel bounds outside of which no camera ray can hit the (padded) scene box: the box corners are
+// projected through the reference camera model dir(u,v) = llc + u h + v vert - origin
+// (gpu_render.cu:952-967), i.e. corner - origin = lambda (a + u h + v vert) solved for
+// (lambda, lambda u, lambda v) in double precision.  A convex box entirely in front of the camera
+// projects into the bounding rectangle of its projected corners; the rectangle is widened by two
+// pixels, which also covers the jitter ((x + jx) / (W - 1) with 0 <= jx < 1).  If any corner is not
+// safely in front, the bounds are the whole frame.  k_primary uses them to end rays that cannot
+// hit before generating them; rays inside the bounds still get the exact per-ray box test.
+void scene_screen_bounds(const FrameConst& fc, int W, int H, int out[4]) {
+    out[0] = 0; out[1] = 0; out[2] = W - 1; out[3] = H - 1;
+    double a[3], h[3], v[3];
+    for (int k = 0; k < 3; ++k) { a[k] = (double)fc.cam_llc[k] - fc.cam_o[k]; h[k] = fc.cam_h[k]; v[k] = fc.cam_v[k]; }
+    auto det3 = [](const double* c0, const double* c1, const double* c2) {
+        return c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c1[0] * (c0[1] * c2[2] - c0[2] * c2[1]) + c2[0] * (c0[1] * c1[2] - c0[2] * c1[1]);
+    };
+    const double det = det3(a, h, v);
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return;
+    double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
+    for (int c = 0; c < 8; ++c) {
+        double p[3];
+        for (int k = 0; k < 3; ++k) p[k] = (double)((c >> k) & 1 ? fc.scene_hi[k] : fc.scene_lo[k]) - fc.cam_o[k];
+        const double lam = det3(p, h, v) / det, lu = det3(a, p, v) / det, lv = det3(a, h, p) / det;
+        if (!(lam > 1e-9) || !std::isfinite(lam)) return;          // a corner beside or behind the camera: no bound
+        const double u = lu / lam, vv = lv / lam;
+        if (!std::isfinite(u) || !std::isfinite(vv)) return;
+        umin = std::min(umin, u); umax = std::max(umax, u); vmin = std::min(vmin, vv); vmax = std::max(vmax, vv);
+    }
+    auto clampi = [](double x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : (int)x); };
+    out[0] = clampi(std::floor(umin * (W - 1)) - 3.0, 0, W - 1);
+    out[2] = clampi(std::ceil(umax * (W - 1)) + 2.0, 0, W - 1);
+    out[1] = clampi(std::floor(vmin * (H - 1)) - 3.0, 0, H - 1);
+    out[3] = clampi(std::ceil(vmax * (H - 1)) + 2.0, 0, H - 1);
+}
+
 void fill_camera(const DsrtCamera* cam, FrameConst& fc) {
     const DsrtVec3* src[4] = {&cam->origin, &cam->lower_left_corner, &cam->horizontal, &cam->vertical};
     float* dst[4] = {fc.cam_o, fc.cam_llc, fc.cam_h, fc.cam_v};
@@ -473,9 +507,16 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     fill_camera(camera, fc);
     fc.W = W; fc.H = H;
     fc.x0 = x0; fc.y0 = y0; fc.rw = x1 - x0; fc.rh = y1 - y0;
+    {
+        int hb[4];
+        scene_screen_bounds(fc, W, H, hb);
+        fc.hit_x0 = hb[0]; fc.hit_y0 = hb[1]; fc.hit_x1 = hb[2]; fc.hit_y1 = hb[3];
+    }
     fc.tiles_x = (fc.rw + 7) / 8;
     const int tiles_y = (fc.rh + 3) / 4;
     fc.slots_per_sample = fc.tiles_x * tiles_y * 32;
+    fc.inv_tiles_x = 1.0f / (float)fc.tiles_x;
+    fc.inv_slots_per_sample = 1.0f / (float)fc.slots_per_sample;
     fc.spp_total = spp_total;
     fc.max_depth = params->max_depth > 0 ? params->max_depth : 12;
     fc.rng_mode = rng_mode;

@@ -43,7 +43,10 @@ struct FrameConst {
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
     int W, H;
     int x0, y0, rw, rh;               // render rectangle
+    int hit_x0, hit_y0, hit_x1, hit_y1;   // pixels outside [hit_x0, hit_x1] x [hit_y0, hit_y1] cannot see the triangles:
+                                      // the screen-space bounds of the scene box, padded (api.cu: scene_screen_bounds)
     int tiles_x, slots_per_sample;    // 8x4-pixel tiles; slots = tiles*32
+    float inv_tiles_x, inv_slots_per_sample;   // 1/x as floats: quotient estimates for path -> (sample, tile, pixel)
     // estimator
     int spp_total, max_depth, rng_mode;
     uint32_t seed_lo, seed_hi;
