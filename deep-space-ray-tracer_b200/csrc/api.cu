@@ -7,6 +7,7 @@
 #include "dsrt.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -667,6 +668,30 @@ extern "C" int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_f
     if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
     *device_ptr = ctx->accum;
     *num_floats = (size_t)ctx->W * ctx->H * 3;
+    return DSRT_OK;
+}
+
+// ncclReduce resolved at run time: ncclResult_t ncclReduce(const void*, void*, size_t, ncclDataType_t,
+// ncclRedOp_t, int root, ncclComm_t, cudaStream_t); ncclFloat = 7, ncclSum = 0 (nccl.h, stable ABI).
+extern "C" int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root) {
+    if (!ctx || !nccl_comm || root < 0) return DSRT_EINVAL;
+    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    typedef int (*reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+    static reduce_fn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = reinterpret_cast<reduce_fn>(dlsym(h, "ncclReduce"));
+        if (!fn) {
+            const char* why = dlerror();
+            return fail(ctx, DSRT_EUNSUPPORTED, "dsrt_reduce_accum: libnccl not found (%s)", why ? why : "no ncclReduce symbol");
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t nf = (size_t)ctx->W * ctx->H * 3;
+    const int rc = fn(ctx->accum, ctx->accum, nf, /*ncclFloat*/ 7, /*ncclSum*/ 0, root, nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, DSRT_ECUDA, "ncclReduce failed with code %d", rc);
+    CK(cudaStreamSynchronize(ctx->stream));
     return DSRT_OK;
 }
 

@@ -360,11 +360,7 @@ int sample_worker(int g, int G, int id_fd, int out_fd, const Options& o, const S
             dsrt_frame_stats(ctx, &fs);
             // every worker takes part in the reduce even after a failed render (a zero buffer), so the
             // collective cannot dead-lock
-            void* acc = nullptr; size_t nf = 0;
-            if (dsrt_accum_device(ctx, &acc, &nf) != DSRT_OK) { ++errors; break; }
-            cudaStream_t st = (cudaStream_t)dsrt_stream(ctx);
-            if (ncclReduce(acc, acc, nf, ncclFloat, ncclSum, 0, comm, st) != ncclSuccess) { ++errors; break; }
-            cudaStreamSynchronize(st);
+            if (dsrt_reduce_accum(ctx, comm, 0) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx)); ++errors; break; }
             results[k].device_ms = rendered ? fs.device_ms : 0.0;
             results[k].rays = rendered ? (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays) : 0.0;
             if (g == 0) {

@@ -118,6 +118,14 @@ int dsrt_readback_accum(dsrt_ctx* ctx, float* dst, size_t bytes);
 /* Device pointer / element count of the accumulation buffer, for an NCCL sum-reduce issued
  * by the caller (single-frame sample sharding). */
 int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_floats);
+/* The exchange step of a sample-sharded frame: ONE ncclReduce(sum, float) of this
+ * ctx's accumulation buffer to rank `root` of `nccl_comm` (an ncclComm_t the caller created for its
+ * ranks, passed as void* so that this header needs no NCCL types), enqueued on the ctx stream and
+ * waited for.  Every rank of the communicator calls it once per frame after dsrt_render_frame with
+ * its own [sample_begin, sample_end); the root then tone-maps with dsrt_readback_rgb8.  libnccl is
+ * looked up at the first call (dlopen), so the library itself does not depend on it;
+ * DSRT_EUNSUPPORTED when it cannot be found. */
+int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root);
 /* Replace the accumulation buffer contents from host memory (root of a host-side reduce). */
 int dsrt_upload_accum(dsrt_ctx* ctx, const float* src, size_t bytes);
 
