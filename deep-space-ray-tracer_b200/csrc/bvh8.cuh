@@ -255,6 +255,9 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
 // average) and is 20 % of the issued instructions; capping it at one or two tests per step, so that
 // the other lanes go on visiting nodes, was measured 15-40 % SLOWER on B200 (C2 traversal 14.5 ->
 // 16.8 ms at two per step, 20.2 ms at one): draining keeps t_max tight for the next node visit.
+// The wait for a triangle record is the hottest single stall of the traversal (13 % of k_trace's
+// samples); prefetching the later records of a group into L1 and fetching two records per trip
+// were both measured slower as well (+3 %: the loop runs at the 64-register cap).
 struct LaneTrav {
     float ox, oy, oz, dx, dy, dz;
     float idx, idy, idz;
