@@ -124,7 +124,7 @@ def parse_args():
     ap.add_argument("--diffuse_only", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
-    ap.add_argument("--cpu_step", type=int, default=8, help="pixel stride of the CPU sample")
+    ap.add_argument("--cpu_step", type=int, default=4, help="pixel stride of the CPU sample")
     ap.add_argument("--spb", type=int, default=0, help="samples of a pixel in flight together (0 = library default)")
     ap.add_argument("--config", default="", choices=["", "c2", "c4", "c5"],
                     help="BASELINE.json presets: c2 = the default; c4 = 3840x2160, 1000 spp (use with --mode sample); "
@@ -398,12 +398,13 @@ def cpu_baseline(a, tris, mats, poses):
     cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
     step = max(1, a.cpu_step)
     cores = os.cpu_count() or 1
-    sample = f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, 2 of {a.spp} samples, depth {a.depth}"
+    ns = min(8, a.spp)
+    sample = f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, {ns} of {a.spp} samples, depth {a.depth}"
     try:
         import refcpu
         if refcpu.available():
             sc = refcpu.RefCpuScene(tris, mats)
-            secs, c = sc.render(cam_pos, sun, a.width, a.height, a.spp, a.depth, step_x=step, step_y=step, s_begin=0, s_end=2, threads=cores)
+            secs, c = sc.render(cam_pos, sun, a.width, a.height, a.spp, a.depth, step_x=step, step_y=step, s_begin=0, s_end=ns, threads=cores)
             return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
                     "sample": sample, "bvh_build_s": sc.build_s, "seconds": secs}
         import oracle
@@ -412,10 +413,10 @@ def cpu_baseline(a, tris, mats, poses):
         cam = d.camera_look_at_origin(cam_pos, 40.0, w, h)
         cam12 = np.array(cam.origin.tuple() + cam.lower_left_corner.tuple() + cam.horizontal.tuple() + cam.vertical.tuple(), np.float32)
         t0 = time.perf_counter()
-        _, _, c = sc.render(cam12, w, h, a.spp, a.depth, sun, rng_mode=1, s_begin=0, s_end=2)
+        _, _, c = sc.render(cam12, w, h, a.spp, a.depth, sun, rng_mode=1, s_begin=0, s_end=ns)
         secs = time.perf_counter() - t0
         return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                "sample": f"{w}x{h} down-sampled frame, 2 of {a.spp} samples, depth {a.depth}", "seconds": secs}
+                "sample": f"{w}x{h} down-sampled frame, {ns} of {a.spp} samples, depth {a.depth}", "seconds": secs}
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
 
