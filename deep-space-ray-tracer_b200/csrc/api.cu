@@ -69,6 +69,7 @@ struct dsrt_ctx {
     int stage_timing = 0;
     int spb_override = 0;
     int builder = DSRT_BUILDER_PLOC;   // binary-tree stage of the BVH build (bvh_build.h)
+    int work_gb = 20;                  // work-memory budget of a batch in GB (DSRT_WORK_GB)
     int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
     cudaEvent_t ev_frame[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
@@ -209,6 +210,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     }
     launch_dims(&ctx->dims, device);
     if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);      // tuning experiments only
+    if (const char* e = getenv("DSRT_WORK_GB")) ctx->work_gb = std::max(1, std::min(120, atoi(e)));
     if (const char* e = getenv("DSRT_BVH_BUILDER")) ctx->builder = strcmp(e, "lbvh") == 0 ? DSRT_BUILDER_LBVH : DSRT_BUILDER_PLOC;
     *out = ctx;
     return DSRT_OK;
@@ -531,13 +533,13 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
 
     // Samples of a pixel in flight together.  Large batches keep the deep-bounce launches
     // (few surviving rays) big enough to fill the GPU (profiles/r01_a: 2x from spb 4 -> 32);
-    // the default takes as many samples as fit a ~20 GB work-memory budget (144 B per path).
+    // the default takes as many samples as fit the work-memory budget (144 B per path; ctx->work_gb).
     int spb = 1;
     const int nsamples = sample_end - sample_begin;
     if (rng_mode == DSRT_RNG_PHILOX) {
         if (ctx->spb_override > 0) spb = ctx->spb_override;
         else {
-            const long long target = 20ll * 1000 * 1000 * 1000 / 144;
+            const long long target = (long long)ctx->work_gb * 1000 * 1000 * 1000 / 144;
             spb = (int)std::max(1ll, std::min(256ll, target / std::max(1, fc.slots_per_sample)));
         }
         spb = std::max(1, std::min(spb, std::max(1, nsamples)));

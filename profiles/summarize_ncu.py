@@ -51,6 +51,17 @@ def launches(path):
     print(f"# {len(order)} launches, {tot:.1f} us summed (ncu: cold-cache, serialised -- compare SHARES)")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:48s} n={v[0]:5d} total={v[1]:11.1f} us share={v[1] / tot:6.3f}")
+    # shares within the render step only (this library's frame kernels), to set beside bench.py's
+    # kernel_ms_per_step / ms_per_step
+    step = ("k_batch_begin", "k_primary", "k_shade", "k_advance", "k_trace", "k_tail", "k_resolve", "k_tonemap")
+    sagg = {k: v for k, v in agg.items() if k.split("<")[0] in step}
+    stot = sum(v[1] for v in sagg.values())
+    if stot > 0:
+        print(f"# render-step kernels only: {stot:.1f} us summed")
+        for k, v in sorted(sagg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {k:46s} n={v[0]:5d} total={v[1]:11.1f} us share_of_step={v[1] / stot:6.3f}")
+        trav = sum(v[1] for k, v in sagg.items() if k.split("<")[0] in ("k_primary", "k_trace", "k_tail"))
+        print(f"  traversal kernels (k_primary + k_trace + k_tail) share_of_step={trav / stot:6.3f}")
     print("# first 60 launches in order")
     for n, v in order[:60]:
         print(f"  {n:46s} {v:10.1f} us")

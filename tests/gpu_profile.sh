@@ -8,7 +8,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo 
 tail -3 gpurun_out/pytest_gpu_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench_rc=$?
 cat gpurun_out/bench_$TAG.json
-PROF="python bench.py --steps 1 --warmup 1 --spp 16 --no_cpu_baseline --no_e2e"
+PROF="python bench.py --steps 1 --warmup 1 --spp 16 --no_cpu_baseline --no_e2e --no_ref_gpu"
 $PROF > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv $PROF > gpurun_out/ncu1_$TAG.log 2>&1
 echo ncu1_rc=$?
