@@ -69,7 +69,7 @@ struct dsrt_ctx {
     int stage_timing = 0;
     int spb_override = 0;
     int builder = DSRT_BUILDER_PLOC;   // binary-tree stage of the BVH build (bvh_build.h)
-    int work_gb = 20;                  // work-memory budget of a batch in GB (DSRT_WORK_GB)
+    int work_gb = 60;                  // work-memory budget of a batch in GB, a third of a B200's HBM (DSRT_WORK_GB)
     int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
     cudaEvent_t ev_frame[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
@@ -543,8 +543,20 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
             spb = (int)std::max(1ll, std::min(256ll, target / std::max(1, fc.slots_per_sample)));
         }
         spb = std::max(1, std::min(spb, std::max(1, nsamples)));
+        // equal batches: 250 samples at a limit of 200 run as 125 + 125, not 200 + 50
+        if (ctx->spb_override <= 0 && nsamples > spb) {
+            const int nb = (nsamples + spb - 1) / spb;
+            spb = (nsamples + nb - 1) / nb;
+        }
     }
-    rc = ensure_work(ctx, (size_t)fc.slots_per_sample * spb);
+    // The budget is a wish, not a requirement: when the device cannot give that much (another
+    // process on the GPU), halve the batch until the allocation succeeds.
+    for (;;) {
+        rc = ensure_work(ctx, (size_t)fc.slots_per_sample * spb);
+        if (rc == DSRT_OK || spb == 1 || rng_mode != DSRT_RNG_PHILOX) break;
+        cudaGetLastError();           // clear the allocation failure
+        spb = (spb + 1) / 2;
+    }
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) { fc.rq_o[k] = ctx->rq_o[k]; fc.rq_d[k] = ctx->rq_d[k]; }
     fc.hits = ctx->hits; fc.st_a = ctx->st_a; fc.st_b = ctx->st_b; fc.sq_o = ctx->sq_o; fc.sq_l = ctx->sq_l;
