@@ -134,11 +134,6 @@ __device__ __forceinline__ void load_tri_record(const float4* tp, float4& ra, fl
                  : "=f"(rc.x), "=f"(rc.y), "=f"(rc.z), "=f"(rc.w) : "l"(tp));
 }
 
-__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
-    // each byte: 0x80 set -> 0xFF, else 0x00
-    return ((x >> 7) & 0x01010101u) * 0xFFu;
-}
-
 // Byte j of a packed plane word as the float 1 + q * 2^-15: one PRMT drops the byte into
 // mantissa bits 8..15 of 1.0f (0x3F800000).  `one` must live in a register so that the PRMT
 // selector can be the instruction's immediate; the caller gets it from memory the compiler
