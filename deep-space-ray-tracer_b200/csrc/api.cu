@@ -429,7 +429,7 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
 // pixels, which also covers the jitter ((x + jx) / (W - 1) with 0 <= jx < 1).  If any corner is not
 // safely in front, the bounds are the whole frame.  k_primary uses them to end rays that cannot
 // hit before generating them; rays inside the bounds still get the exact per-ray box test.
-void scene_screen_bounds(const FrameConst& fc, int W, int H, int out[4]) {
+bool scene_screen_bounds(const FrameConst& fc, int W, int H, int out[4]) {
     out[0] = 0; out[1] = 0; out[2] = W - 1; out[3] = H - 1;
     double a[3], h[3], v[3];
     for (int k = 0; k < 3; ++k) { a[k] = (double)fc.cam_llc[k] - fc.cam_o[k]; h[k] = fc.cam_h[k]; v[k] = fc.cam_v[k]; }
@@ -437,15 +437,15 @@ void scene_screen_bounds(const FrameConst& fc, int W, int H, int out[4]) {
         return c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c1[0] * (c0[1] * c2[2] - c0[2] * c2[1]) + c2[0] * (c0[1] * c1[2] - c0[2] * c1[1]);
     };
     const double det = det3(a, h, v);
-    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return;
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return false;
     double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
     for (int c = 0; c < 8; ++c) {
         double p[3];
         for (int k = 0; k < 3; ++k) p[k] = (double)((c >> k) & 1 ? fc.scene_hi[k] : fc.scene_lo[k]) - fc.cam_o[k];
         const double lam = det3(p, h, v) / det, lu = det3(a, p, v) / det, lv = det3(a, h, p) / det;
-        if (!(lam > 1e-9) || !std::isfinite(lam)) return;          // a corner beside or behind the camera: no bound
+        if (!(lam > 1e-9) || !std::isfinite(lam)) return false;          // a corner beside or behind the camera: no bound
         const double u = lu / lam, vv = lv / lam;
-        if (!std::isfinite(u) || !std::isfinite(vv)) return;
+        if (!std::isfinite(u) || !std::isfinite(vv)) return false;
         umin = std::min(umin, u); umax = std::max(umax, u); vmin = std::min(vmin, vv); vmax = std::max(vmax, vv);
     }
     auto clampi = [](double x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : (int)x); };
@@ -453,6 +453,7 @@ void scene_screen_bounds(const FrameConst& fc, int W, int H, int out[4]) {
     out[2] = clampi(std::ceil(umax * (W - 1)) + 2.0, 0, W - 1);
     out[1] = clampi(std::floor(vmin * (H - 1)) - 3.0, 0, H - 1);
     out[3] = clampi(std::ceil(vmax * (H - 1)) + 2.0, 0, H - 1);
+    return true;
 }
 
 void fill_camera(const DsrtCamera* cam, FrameConst& fc) {
@@ -512,8 +513,9 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     fc.x0 = x0; fc.y0 = y0; fc.rw = x1 - x0; fc.rh = y1 - y0;
     {
         int hb[4];
-        scene_screen_bounds(fc, W, H, hb);
+        const bool bounded = scene_screen_bounds(fc, W, H, hb);
         fc.hit_x0 = hb[0]; fc.hit_y0 = hb[1]; fc.hit_x1 = hb[2]; fc.hit_y1 = hb[3];
+        fc.cull_pixels = (bounded && fc.num_spheres == 0 && rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
     }
     fc.tiles_x = (fc.rw + 7) / 8;
     const int tiles_y = (fc.rh + 3) / 4;

@@ -43,6 +43,7 @@ struct FrameConst {
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
     int W, H;
     int x0, y0, rw, rh;               // render rectangle
+    int cull_pixels;                  // 1: the bounds below are in force (Philox stream, no spheres, scene box in front of the camera)
     int hit_x0, hit_y0, hit_x1, hit_y1;   // pixels outside [hit_x0, hit_x1] x [hit_y0, hit_y1] cannot see the triangles:
                                       // the screen-space bounds of the scene box, padded (api.cu: scene_screen_bounds)
     int tiles_x, slots_per_sample;    // 8x4-pixel tiles; slots = tiles*32
