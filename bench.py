@@ -229,7 +229,8 @@ def run_dsrt(a, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     params = d.make_params(a.width, a.height, a.spp, a.depth, d.RNG_PHILOX)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    rgb = np.empty((a.height, a.width, 3), np.uint8)
+    # the e2e leg reads every frame back into page-locked host memory (the caller's buffer; any host pointer works)
+    rgb = torch.empty((a.height, a.width, 3), dtype=torch.uint8, pin_memory=True).numpy()
 
     def frame_inputs(i):
         # frame-parallel: step i covers frames i*world .. i*world+world-1, rank r takes its own

@@ -653,6 +653,16 @@ extern "C" int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out) {
     return DSRT_OK;
 }
 
+extern "C" int dsrt_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return DSRT_EINVAL;
+    *ptr = nullptr;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? DSRT_OK : DSRT_ENOMEM;
+}
+
+extern "C" void dsrt_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 extern "C" int dsrt_readback_rgb8(dsrt_ctx* ctx, int total_spp, float gamma, unsigned char* dst, size_t bytes) {
     if (!ctx || !dst) return DSRT_EINVAL;
     if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");

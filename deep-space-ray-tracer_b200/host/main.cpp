@@ -154,29 +154,59 @@ DsrtRenderParams make_params(const Options& o) {
     return p;
 }
 
-bool save_frame(const Options& o, size_t index, const std::vector<unsigned char>& rgb) {
+bool save_frame(const Options& o, size_t index, const unsigned char* rgb) {
     char name[64];
     std::snprintf(name, sizeof(name), "frame_%04zu.ppm", index);
     const std::string ppm = o.out_dir + "/" + name;
     std::snprintf(name, sizeof(name), "frame_%04zu.png", index);
     const std::string png = o.out_dir + "/" + name;
-    if (dsrt_write_ppm(ppm.c_str(), rgb.data(), o.width, o.height) != DSRT_OK) return false;
-    if (o.png && dsrt_write_png(png.c_str(), rgb.data(), o.width, o.height) != DSRT_OK) return false;
+    if (dsrt_write_ppm(ppm.c_str(), rgb, o.width, o.height) != DSRT_OK) return false;
+    if (o.png && dsrt_write_png(png.c_str(), rgb, o.width, o.height) != DSRT_OK) return false;
     return true;
 }
 
 std::mutex g_print;
 
 // Writes finished frames on its own thread so the GPU that produced them keeps rendering.
-// At most two frames are queued (the producer blocks beyond that).
+// Frames travel in three page-locked buffers that circulate between the render loop (acquire ->
+// read back -> push) and the writer (save -> release), so at most two frames wait to be written
+// and the producer blocks beyond that.  Created after the ctx (page-locked memory needs CUDA).
 class FrameWriter {
 public:
-    FrameWriter(const Options& o, std::vector<FrameResult>& results) : o_(o), results_(results), th_([this] { run(); }) {}
-    ~FrameWriter() { finish(); }
-    void push(size_t slot, size_t index, std::vector<unsigned char>&& rgb) {
+    FrameWriter(const Options& o, std::vector<FrameResult>& results)
+        : o_(o), results_(results), bytes_((size_t)o.width * o.height * 3) {
+        for (int k = 0; k < 3; ++k) {
+            void* p = nullptr;
+            if (dsrt_host_alloc(&p, bytes_) != DSRT_OK) { p = std::malloc(bytes_); pageable_.push_back(p); }
+            all_.push_back((unsigned char*)p);
+            free_.push_back((unsigned char*)p);
+        }
+        th_ = std::thread([this] { run(); });
+    }
+    ~FrameWriter() {
+        finish();
+        for (unsigned char* p : all_) {
+            bool pageable = false;
+            for (void* q : pageable_) pageable = pageable || q == p;
+            if (pageable) std::free(p); else dsrt_host_free(p);
+        }
+    }
+    size_t bytes() const { return bytes_; }
+    unsigned char* acquire() {
         std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [this] { return q_.size() < 2; });
-        q_.push_back(Item{slot, index, std::move(rgb)});
+        cv_.wait(l, [this] { return !free_.empty(); });
+        unsigned char* p = free_.back();
+        free_.pop_back();
+        return p;
+    }
+    void release(unsigned char* p) {
+        std::lock_guard<std::mutex> l(mu_);
+        free_.push_back(p);
+        cv_.notify_all();
+    }
+    void push(size_t slot, size_t index, unsigned char* rgb) {
+        std::lock_guard<std::mutex> l(mu_);
+        q_.push_back(Item{slot, index, rgb});
         cv_.notify_all();
     }
     void finish() {
@@ -186,10 +216,10 @@ public:
             closed_ = true;
         }
         cv_.notify_all();
-        th_.join();
+        if (th_.joinable()) th_.join();
     }
 private:
-    struct Item { size_t slot, index; std::vector<unsigned char> rgb; };
+    struct Item { size_t slot, index; unsigned char* rgb; };
     void run() {
         for (;;) {
             Item it;
@@ -197,15 +227,18 @@ private:
                 std::unique_lock<std::mutex> l(mu_);
                 cv_.wait(l, [this] { return !q_.empty() || closed_; });
                 if (q_.empty()) return;
-                it = std::move(q_.front());
+                it = q_.front();
                 q_.pop_front();
-                cv_.notify_all();
             }
             results_[it.slot].done = save_frame(o_, it.index, it.rgb);
+            release(it.rgb);
         }
     }
     const Options& o_;
     std::vector<FrameResult>& results_;
+    size_t bytes_;
+    std::vector<unsigned char*> all_, free_;
+    std::vector<void*> pageable_;
     std::mutex mu_;
     std::condition_variable cv_;
     std::deque<Item> q_;
@@ -246,23 +279,24 @@ void frame_worker(int device, int label, const Options& o, const SceneData& scen
     t0 = std::chrono::high_resolution_clock::now();
     for (size_t k = (size_t)offset; k < jobs.size(); k += (size_t)stride) {
         const FrameJob& j = jobs[k];
-        std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
+        unsigned char* rgb = writer.acquire();
         DsrtCamera cam;
         dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
         int rc = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
-        if (rc == DSRT_OK) rc = dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb.data(), rgb.size());
+        if (rc == DSRT_OK) rc = dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb, writer.bytes());
         if (k == (size_t)offset) times.first_frame_s = seconds_since(t0);
         if (rc != DSRT_OK) {
             std::lock_guard<std::mutex> l(g_print);
             std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, label, dsrt_last_error(ctx));
             ++errors;
+            writer.release(rgb);
             continue;                       // no stale file is renamed into place
         }
         DsrtFrameStats fs;
         dsrt_frame_stats(ctx, &fs);
         results[k].device_ms = fs.device_ms;
         results[k].rays = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
-        writer.push(k, j.index, std::move(rgb));
+        writer.push(k, j.index, rgb);
         std::lock_guard<std::mutex> l(g_print);
         char name[64];
         std::snprintf(name, sizeof(name), "frame_%04zu.png", j.index);
@@ -364,9 +398,9 @@ int sample_worker(int g, int G, int id_fd, int out_fd, const Options& o, const S
             results[k].device_ms = rendered ? fs.device_ms : 0.0;
             results[k].rays = rendered ? (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays) : 0.0;
             if (g == 0) {
-                std::vector<unsigned char> rgb((size_t)o.width * o.height * 3);
-                if (dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb.data(), rgb.size()) != DSRT_OK) { ++errors; continue; }
-                writer.push(k, j.index, std::move(rgb));
+                unsigned char* rgb = writer.acquire();
+                if (dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb, writer.bytes()) != DSRT_OK) { writer.release(rgb); ++errors; continue; }
+                writer.push(k, j.index, rgb);
                 std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, GPU 0: " << fs.device_ms << " ms]\n";
             } else {
                 results[k].done = rendered;

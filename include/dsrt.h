@@ -109,6 +109,12 @@ int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples);
 #define DSRT_BVH_LBVH 1
 int dsrt_set_bvh_builder(dsrt_ctx* ctx, int builder);
 
+/* Page-locked host memory for frame read-backs (optional: every read-back entry accepts any host
+ * pointer; a page-locked destination lets the copy run at full PCIe rate and overlap with the writer
+ * thread's work).  The reference reads back into pageable memory (gpu_render.cu:1086-1092). */
+int dsrt_host_alloc(void** ptr, size_t bytes);
+void dsrt_host_free(void* ptr);
+
 /* Tone-map the accumulation buffer exactly as the reference kernel's tail
  * (gpu_render.cu:1003-1030: mean over total_spp, max 0, min 10, powf(c, 1/gamma), clamp,
  * (uchar)(255.99f*c), row flip) and copy W*H*3 bytes, top row first, to `dst`. */
