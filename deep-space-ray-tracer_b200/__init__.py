@@ -96,7 +96,7 @@ SYMBOLS = [
     "dsrt_scene_upload", "dsrt_scene_upload_device", "dsrt_scene_stats", "dsrt_scene_download",
     "dsrt_render_frame", "dsrt_frame_stats", "dsrt_set_stage_timing", "dsrt_set_samples_per_batch",
     "dsrt_set_bvh_builder",
-    "dsrt_host_alloc", "dsrt_host_free", "dsrt_readback_rgb8", "dsrt_readback_accum", "dsrt_accum_device", "dsrt_upload_accum", "dsrt_reduce_accum",
+    "dsrt_host_alloc", "dsrt_host_free", "dsrt_box_screen_bounds", "dsrt_readback_rgb8", "dsrt_readback_accum", "dsrt_accum_device", "dsrt_upload_accum", "dsrt_reduce_accum",
     "dsrt_trace_closest", "dsrt_trace_occluded", "dsrt_first_hits",
     "dsrt_trace_closest_device", "dsrt_trace_occluded_device",
     "dsrt_read_pose_file", "dsrt_pose_to_model_frame", "dsrt_camera_look_at_origin",

@@ -653,6 +653,16 @@ extern "C" int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out) {
     return DSRT_OK;
 }
 
+extern "C" int dsrt_box_screen_bounds(const DsrtCamera* camera, const float lo[3], const float hi[3],
+                                      int width, int height, int out[4]) {
+    if (!camera || !lo || !hi || !out || width < 2 || height < 2) return 0;
+    FrameConst fc;
+    memset(&fc, 0, sizeof(fc));
+    fill_camera(camera, fc);
+    for (int k = 0; k < 3; ++k) { fc.scene_lo[k] = lo[k]; fc.scene_hi[k] = hi[k]; }
+    return scene_screen_bounds(fc, width, height, out) ? 1 : 0;
+}
+
 extern "C" int dsrt_host_alloc(void** ptr, size_t bytes) {
     if (!ptr || bytes == 0) return DSRT_EINVAL;
     *ptr = nullptr;

@@ -109,6 +109,15 @@ int dsrt_set_samples_per_batch(dsrt_ctx* ctx, int samples);
 #define DSRT_BVH_LBVH 1
 int dsrt_set_bvh_builder(dsrt_ctx* ctx, int builder);
 
+/* Host arithmetic, no device needed (exposed for tests): the inclusive pixel rectangle
+ * out = {x0, y0, x1, y1} (y = 0 is the bottom row, as in the kernel) outside of which no camera ray
+ * of the reference camera model (gpu_render.cu:952-967) can hit the axis-aligned box [lo, hi].
+ * Returns 1 when the rectangle is a real bound, 0 when it is the whole frame because a box corner
+ * is beside or behind the camera.  dsrt_render_frame uses it to end such paths before generating
+ * their rays. */
+int dsrt_box_screen_bounds(const DsrtCamera* camera, const float lo[3], const float hi[3],
+                           int width, int height, int out[4]);
+
 /* Page-locked host memory for frame read-backs (optional: every read-back entry accepts any host
  * pointer; a page-locked destination lets the copy run at full PCIe rate and overlap with the writer
  * thread's work).  The reference reads back into pageable memory (gpu_render.cu:1086-1092). */

@@ -148,3 +148,48 @@ def test_product_never_touches_the_oracle():
         if p.suffix in (".cu", ".cuh", ".h", ".cpp", ".py") or p.name == "Makefile":
             text = p.read_text(errors="ignore")
             assert "liboracle" not in text and "oracle/" not in text and "import oracle" not in text, p
+
+
+def test_box_screen_bounds_are_conservative(dsrt, poses):
+    """dsrt_box_screen_bounds (host arithmetic behind k_primary's early miss): every point of the box,
+    projected with the reference camera model u = (x + jx) / (W - 1) (gpu_render.cu:952-967), must
+    land on a pixel inside the returned rectangle; and when a corner is behind the camera the
+    function must say "no bound"."""
+    import ctypes as C
+    lib = dsrt.lib
+    lib.dsrt_box_screen_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.dsrt_box_screen_bounds.restype = C.c_int
+    rng = np.random.default_rng(3)
+    W, H = 640, 360
+    lo = np.array([-950.0, -420.0, -25.0], np.float32)
+    hi = np.array([950.0, 420.0, 25.0], np.float32)
+    views = [dsrt.pose_to_model_frame(poses[k])[0] for k in (0, 49, 98)] + [np.array(v, np.float32) for v in
+             ((300.0, 120.0, 160.0), (2500.0, 900.0, 700.0), (-1400.0, 30.0, 12.0), (0.0, 0.5, 3.0))]
+    bounded = 0
+    for lookfrom in views:
+        cam = dsrt.camera_look_at_origin(np.asarray(lookfrom, np.float32), 40.0, W, H)
+        out = (C.c_int * 4)()
+        ok = lib.dsrt_box_screen_bounds(C.byref(cam), lo.ctypes.data_as(C.POINTER(C.c_float)), hi.ctypes.data_as(C.POINTER(C.c_float)), W, H, out)
+        x0, y0, x1, y1 = out[:]
+        assert 0 <= x0 <= x1 <= W - 1 and 0 <= y0 <= y1 <= H - 1
+        o = np.array(cam.origin.tuple(), np.float64)
+        a = np.array(cam.lower_left_corner.tuple(), np.float64) - o
+        hvec = np.array(cam.horizontal.tuple(), np.float64)
+        vvec = np.array(cam.vertical.tuple(), np.float64)
+        M = np.stack([a, hvec, vvec], 1)
+        pts = rng.uniform(lo, hi, size=(20000, 3)).astype(np.float64)
+        corners = np.array([[(hi if (c >> k) & 1 else lo)[k] for k in range(3)] for c in range(8)], np.float64)
+        sol = np.linalg.solve(M, (np.concatenate([pts, corners]) - o).T).T          # (lambda, lambda u, lambda v)
+        lam = sol[:, 0]
+        if not ok:
+            assert (x0, y0, x1, y1) == (0, 0, W - 1, H - 1)
+            assert lam[-8:].min() <= 1e-6, "bounds were dropped although every corner is in front of the camera"
+            continue
+        bounded += 1
+        assert lam.min() > 0
+        px = np.floor(sol[:, 1] / lam * (W - 1))          # the pixel whose footprint [px, px + 1) holds the point
+        py = np.floor(sol[:, 2] / lam * (H - 1))
+        vis = (px >= 0) & (px <= W - 1) & (py >= 0) & (py <= H - 1)
+        assert vis.any()
+        assert (px[vis] >= x0).all() and (px[vis] <= x1).all() and (py[vis] >= y0).all() and (py[vis] <= y1).all()
+    assert bounded >= 4
