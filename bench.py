@@ -220,6 +220,8 @@ def run_dsrt(a, rank, world, local_rank):
 
     poses = d.read_pose_file(POSE_FILE)
     tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
+    import hashlib
+    mesh_sha = hashlib.sha256(np.ascontiguousarray(np.stack([np.stack([tris[v][k] for k in "xyz"], 1) for v in ("v0", "v1", "v2")], 1)).tobytes()).hexdigest()
     ctx = d.Context(local_rank)
     st_first = ctx.upload_scene(tris, mats)       # includes one-off module loading and allocator warm-up
     st = ctx.upload_scene(tris, mats)             # the same upload + GPU BVH build again: the repeatable cost
@@ -338,6 +340,9 @@ def run_dsrt(a, rank, world, local_rank):
             "config": {"workload": workload_name(a), "parallelism": f"{a.mode}-parallel x{world}" if world > 1 else "single GPU",
                        "rng": "philox4x32-10", "l2": "flushed between steps (256 MiB write)",
                        "frames_per_s": world * a.steps / (ms * 1e-3) if a.mode == "frame" else a.steps / (ms * 1e-3),
+                       # generator parameters and a SHA-256 of the vertex buffer go with every number
+                       "mesh": {"generator": "dsrt_synth_mesh", "seed": 1337, "triangles": int(a.tris), "diffuse_only": bool(a.diffuse_only),
+                                "vertices_sha256": mesh_sha},
                        "bvh": {"wide_nodes": st.num_wide_nodes, "levels": st.num_levels, "build_ms": st.build_ms,
                                "build_ms_first_call": st_first.build_ms, "upload_ms": st.upload_ms, "sah": st.sah_cost,
                                "builder": os.environ.get("DSRT_BVH_BUILDER", "ploc")}},
