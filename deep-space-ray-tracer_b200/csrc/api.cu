@@ -55,6 +55,9 @@ struct dsrt_ctx {
     float* accum = nullptr;
     uint32_t* rng_pix = nullptr;
     unsigned char* d_rgb = nullptr;
+    uint2* tile_table = nullptr;       // per-tile traversal entry groups of the current frame (render.cu: k_tile_entries)
+    size_t tile_table_tiles = 0;
+    int use_tile_entries = 1;
     int lcg_next_sample = -1;
 
     size_t cap_paths = 0;
@@ -210,6 +213,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     }
     launch_dims(&ctx->dims, device);
     if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);      // tuning experiments only
+    if (const char* e = getenv("DSRT_TILE_ENTRIES")) ctx->use_tile_entries = atoi(e) != 0;     // A/B runs
     if (const char* e = getenv("DSRT_WORK_GB")) ctx->work_gb = std::max(1, std::min(120, atoi(e)));
     if (const char* e = getenv("DSRT_BVH_BUILDER")) ctx->builder = strcmp(e, "lbvh") == 0 ? DSRT_BUILDER_LBVH : DSRT_BUILDER_PLOC;
     *out = ctx;
@@ -222,7 +226,7 @@ extern "C" void dsrt_destroy(dsrt_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     free_work(ctx);
-    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb);
+    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb); cudaFree(ctx->tile_table);
     cudaFree(ctx->counters); cudaFree(ctx->stats);
     cudaFree(ctx->t_rays); cudaFree(ctx->t_hits); cudaFree(ctx->t_occ);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -569,6 +573,22 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
 
     CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * S_COUNT, ctx->stream));
     CK(cudaEventRecord(ctx->ev_frame[0], ctx->stream));
+
+    // traversal entry points of the camera rays, per 8x4-pixel tile of the rectangle (part of the frame's device time)
+    fc.tile_entries = nullptr;
+    fc.cull_tiles = 0;
+    if (ctx->use_tile_entries && fc.num_nodes > 0) {
+        const size_t ntiles = (size_t)fc.slots_per_sample >> 5;
+        if (ntiles > ctx->tile_table_tiles) {
+            cudaFree(ctx->tile_table);
+            ctx->tile_table = nullptr; ctx->tile_table_tiles = 0;
+            CK(cudaMalloc(&ctx->tile_table, ntiles * sizeof(uint2)));
+            ctx->tile_table_tiles = ntiles;
+        }
+        launch_tile_entries(fc, ctx->tile_table, ctx->stream);
+        fc.tile_entries = ctx->tile_table;
+        fc.cull_tiles = (fc.num_spheres == 0 && rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
+    }
 
     uint32_t launches = 0, batches = 0;
     size_t nev = 0;                 // events used from the pool

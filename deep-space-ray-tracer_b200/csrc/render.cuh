@@ -43,6 +43,9 @@ struct FrameConst {
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
     int W, H;
     int x0, y0, rw, rh;               // render rectangle
+    const uint2* tile_entries;        // per 8x4-pixel tile: the node group its camera rays start from (k_tile_entries),
+                                      // y == 0: the tile cannot hit a triangle; nullptr = every ray starts at the root
+    int cull_tiles;                   // 1: a tile with no entries is skipped outright (Philox stream, no spheres)
     int cull_pixels;                  // 1: the bounds below are in force (Philox stream, no spheres, scene box in front of the camera)
     int hit_x0, hit_y0, hit_x1, hit_y1;   // pixels outside [hit_x0, hit_x1] x [hit_y0, hit_y1] cannot see the triangles:
                                       // the screen-space bounds of the scene box, padded (api.cu: scene_screen_bounds)
@@ -78,6 +81,8 @@ struct LaunchDims {
 // Host-callable launchers (all asynchronous on `s`).
 void launch_dims(LaunchDims* d, int device);
 void launch_batch_begin(const FrameConst& fc, cudaStream_t s);
+// Fills `table` (one uint2 per 8x4-pixel tile of the render rectangle) with the node the rays of each tile start from.
+void launch_tile_entries(const FrameConst& fc, uint2* table, cudaStream_t s);
 void launch_primary(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_trace(const FrameConst& fc, int cur, int shadow_slot, const LaunchDims& d, cudaStream_t s);
 void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
