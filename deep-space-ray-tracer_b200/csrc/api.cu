@@ -575,6 +575,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     CK(cudaEventRecord(ctx->ev_frame[0], ctx->stream));
 
     // traversal entry points of the camera rays, per 8x4-pixel tile of the rectangle (part of the frame's device time)
+    uint32_t tile_launches = 0;
     fc.tile_entries = nullptr;
     fc.cull_tiles = 0;
     if (ctx->use_tile_entries && fc.num_nodes > 0) {
@@ -586,11 +587,12 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
             ctx->tile_table_tiles = ntiles;
         }
         launch_tile_entries(fc, ctx->tile_table, ctx->stream);
+        tile_launches = 1;
         fc.tile_entries = ctx->tile_table;
         fc.cull_tiles = (fc.num_spheres == 0 && rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
     }
 
-    uint32_t launches = 0, batches = 0;
+    uint32_t launches = tile_launches, batches = 0;
     size_t nev = 0;                 // events used from the pool
     std::vector<int> ev_kind;       // what the interval [k, k+1) measured: 0 k_trace, 1 k_shade, 2 k_primary, -1 other
     const bool timing = ctx->stage_timing != 0;
