@@ -196,8 +196,10 @@ def test_depth_and_sun_switches(dsrt, poses, ctx):
     assert fs0.rays == fs12.rays
 
 
-@pytest.mark.parametrize("frame,lookfrom", [(0, None), (98, None), (None, (300.0, 120.0, 160.0)), (None, (-1400.0, 30.0, 12.0))])
-def test_philox_frames_vs_oracle_across_views(dsrt, poses, ctx, oracle_scene10k, frame, lookfrom):
+@pytest.mark.parametrize("frame,lookfrom,vfov", [(0, None, 40.0), (98, None, 40.0), (None, (300.0, 120.0, 160.0), 40.0),
+                                                 (None, (-1400.0, 30.0, 12.0), 40.0), (None, (200.0, 100.0, 10.0), 40.0),
+                                                 (None, (40.0, -20.0, 60.0), 110.0)])
+def test_philox_frames_vs_oracle_across_views(dsrt, poses, ctx, oracle_scene10k, frame, lookfrom, vfov):
     """The Philox path skips ray generation for pixels outside the screen-space bounds of the scene
     box (api.cu: scene_screen_bounds).  Far pose (station small in the frame), closest pose, a view
     from inside the box's slab with the station filling the frame, and a grazing view along the
@@ -208,7 +210,7 @@ def test_philox_frames_vs_oracle_across_views(dsrt, poses, ctx, oracle_scene10k,
         _, sun, cam = pose_cam(dsrt, poses, frame, w, h, spp, DEPTH)
     else:
         _, sun, _ = pose_cam(dsrt, poses, 0, w, h, spp, DEPTH)
-        cam = dsrt.camera_look_at_origin(np.array(lookfrom, np.float32), 40.0, w, h, spp, DEPTH)
+        cam = dsrt.camera_look_at_origin(np.array(lookfrom, np.float32), vfov, w, h, spp, DEPTH)
     fs = ctx.render(cam, sun, dsrt.make_params(w, h, spp, DEPTH, dsrt.RNG_PHILOX))
     assert fs.primary_rays == w * h * spp
     acc = ctx.readback_accum()
@@ -218,6 +220,11 @@ def test_philox_frames_vs_oracle_across_views(dsrt, poses, ctx, oracle_scene10k,
     assert np.abs(acc - oacc).mean() < 0.02
     # pixels the oracle finds black must be black here too, and vice versa, up to libm-level flips
     assert ((acc.sum(2) > 0) != (oacc.sum(2) > 0)).mean() <= 0.01
+    # the LCG replay takes the same entry points (no culling there: its generator has to advance per pixel)
+    ctx.render(cam, sun, dsrt.make_params(w, h, spp, DEPTH, dsrt.RNG_REF_LCG))
+    limg = ctx.readback_rgb8(spp, 2.0)
+    _, lrgb, _ = oracle_scene10k.render(cam12_of(cam), w, h, spp, DEPTH, sun, rng_mode=1)
+    assert (limg == lrgb).all(2).mean() >= 0.995, (limg != lrgb).any(2).sum()
 
 
 def test_builders_on_duplicate_and_degenerate_triangles(dsrt):
