@@ -583,7 +583,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
         if (ntiles > ctx->tile_table_tiles) {
             cudaFree(ctx->tile_table);
             ctx->tile_table = nullptr; ctx->tile_table_tiles = 0;
-            CK(cudaMalloc(&ctx->tile_table, ntiles * sizeof(uint2)));
+            CK(cudaMalloc(&ctx->tile_table, ntiles * 8 * sizeof(uint2)));       // up to 8 start nodes per tile (render.cu: DSRT_TILE_ENTRY_COUNT)
             ctx->tile_table_tiles = ntiles;
         }
         launch_tile_entries(fc, ctx->tile_table, ctx->stream);
