@@ -275,7 +275,7 @@ def run_dsrt(a, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms = rays = launches = ext_ms = ext_rays = prim_ms = shade_ms = 0.0
+    ms = rays = launches = ext_ms = ext_rays = prim_ms = shade_ms = culled = 0.0
     for i in range(a.steps):
         m, fs = step(a.warmup + i, True)
         ms += m
@@ -285,6 +285,7 @@ def run_dsrt(a, rank, world, local_rank):
         prim_ms += fs.primary_ms
         shade_ms += fs.shade_ms
         ext_rays += fs.rays
+        culled += fs.culled_primary_rays
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -356,6 +357,10 @@ def run_dsrt(a, rank, world, local_rank):
                          "bytes_per_ray": bpr, "rays_per_step": ext_rays / world / a.steps,
                          "kernel_ms_per_step": ext_ms / a.steps, "k_primary_ms_per_step": prim_ms / a.steps,
                          "k_shade_ms_per_step": shade_ms / a.steps, "traffic": traffic,
+                         # of rays_per_step (rank 0's steps): camera rays whose 8x4-pixel tile provably sees no triangle
+                         # and that ended as misses without a traversal; the rest were traversed
+                         "culled_primary_rays_per_step": culled / a.steps,
+                         "traversed_mrays_per_s": ((ext_rays / world - culled) / (ext_ms * 1e-3) / 1e6) if ext_ms else None,
                          # what actually moved, next to the algorithmic figure: DRAM and L2->SM bytes of the same launches
                          # (ncu, profiles/trace_ncu_summary.json) over the live kernel time
                          "traffic_gbs": (traffic / (ext_ms / a.steps * 1e-3) / 1e9) if traffic and ext_ms else None,

@@ -81,7 +81,7 @@ class FrameStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("paths", C.c_uint64), ("kernel_launches", C.c_uint32), ("batches", C.c_uint32),
                 ("device_ms", C.c_float), ("extend_ms", C.c_float), ("primary_ms", C.c_float),
-                ("shade_ms", C.c_float)]
+                ("shade_ms", C.c_float), ("culled_primary_rays", C.c_uint64)]
 
     @property
     def rays(self):

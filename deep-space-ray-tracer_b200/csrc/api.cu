@@ -651,6 +651,7 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
     fs.bounce_rays = hs[S_BOUNCE];
     fs.shadow_rays = hs[S_SHADOW];
     fs.paths = hs[S_PATHS];
+    fs.culled_primary_rays = hs[S_CULLED];
     fs.kernel_launches = launches;
     fs.batches = batches;
     cudaEventElapsedTime(&fs.device_ms, ctx->ev_frame[0], ctx->ev_frame[1]);

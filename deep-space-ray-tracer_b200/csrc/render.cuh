@@ -20,7 +20,7 @@ enum {
     C_ZERO = 7,       // always 0 (an opaque zero for the traversal kernels, see trace_loop)
     C_COUNT = 8
 };
-enum { S_PRIMARY = 0, S_BOUNCE = 1, S_SHADOW = 2, S_PATHS = 3, S_COUNT = 4 };
+enum { S_PRIMARY = 0, S_BOUNCE = 1, S_SHADOW = 2, S_PATHS = 3, S_CULLED = 4, S_COUNT = 5 };
 
 // Everything a frame's kernels need, passed by value as a __grid_constant__ parameter so
 // that every field is a constant-bank read (the reference dereferences a GPUScene* in

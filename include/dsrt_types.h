@@ -129,6 +129,8 @@ typedef struct DsrtFrameStats {
     float    primary_ms;         /* k_primary alone (included in extend_ms; the sun shadow rays are
                                     traced inside k_trace and have no time of their own) */
     float    shade_ms;           /* k_shade */
+    uint64_t culled_primary_rays; /* of primary_rays: pixel samples whose tile (or pixel) provably cannot see a
+                                    triangle and that ended as misses without a traversal (k_tile_entries) */
 } DsrtFrameStats;
 
 #ifdef __cplusplus
