@@ -366,7 +366,7 @@ def run_dsrt(a, rank, world, local_rank):
                          "traffic_gbs": (traffic / (ext_ms / a.steps * 1e-3) / 1e9) if traffic and ext_ms else None,
                          "l2_to_sm_read_gbs": (l2_read / (ext_ms / a.steps * 1e-3) / 1e9) if l2_read and ext_ms else None,
                          "note": "the 1M-triangle scene (57 MB of nodes and records) is L2-resident, so the traversal is bound by "
-                                 "instruction issue / the ALU pipe, not by HBM (profiles/r01_az_trace_ncu.txt: issue 60-75 %, ALU 50-56 %); "
+                                 "instruction issue / the ALU pipe, not by HBM (profiles/r01_be_trace_ncu.txt: issue 60-75 %, ALU 50-56 %); "
                                  "achieved counts SURVEY 8(d)'s algorithmic bytes, most of which the caches serve"},
         }
         if world == 1 and not a.no_cpu_baseline:
