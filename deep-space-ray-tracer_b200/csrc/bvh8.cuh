@@ -52,7 +52,10 @@ namespace dsrt {
 constexpr int kNodeWords = 6;          // uint4 words per node
 constexpr int kTriWords = 3;           // float4 words per triangle record
 constexpr int kMaxLeafTris = 3;
-constexpr int kSmemStack = 8;          // stack entries per thread kept in shared memory
+#ifndef DSRT_SMEM_STACK
+#define DSRT_SMEM_STACK 8
+#endif
+constexpr int kSmemStack = DSRT_SMEM_STACK;          // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 40;        // overflow entries per thread in local memory
 
 struct TravRay {
