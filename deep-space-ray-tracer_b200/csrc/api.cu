@@ -403,6 +403,7 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
     fc.nodes = ctx->bvh.nodes;
     fc.tri_records = ctx->bvh.tri_records;
     fc.shade_records = ctx->bvh.shade_records;
+    fc.shade_compact = ctx->bvh.shade_compact ? 1 : 0;
     fc.uv_records = ctx->bvh.uv_records;
     fc.materials = ctx->d_mats;
     fc.textures = ctx->d_tex;

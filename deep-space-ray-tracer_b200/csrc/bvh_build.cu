@@ -601,6 +601,32 @@ __global__ void k_shade_records(const DsrtTriangle* __restrict__ tris, int n,
     }
 }
 
+// flag[0] is set when some triangle cannot use the one-word shading record: its three vertex normals
+// differ in some bit, or an id does not fit 16 bits.
+__global__ void k_check_flat_normals(const DsrtTriangle* __restrict__ tris, int n, uint32_t* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tris + i);
+    const int* pi = reinterpret_cast<const int*>(tris + i);
+    bool bad = false;
+    for (int k = 0; k < 3; ++k) bad = bad || p[9 + k] != p[12 + k] || p[9 + k] != p[15 + k];
+    bad = bad || pi[27] < 0 || pi[27] >= 65535 || pi[28] < -1 || pi[28] >= 65534;
+    if (bad) flag[0] = 1u;
+}
+
+__global__ void k_shade_records_compact(const DsrtTriangle* __restrict__ tris, int n,
+                                        float4* __restrict__ shade, float4* __restrict__ uvrec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(tris + i);
+    const int* pi = reinterpret_cast<const int*>(tris + i);
+    shade[i] = make_float4(p[9], p[10], p[11], __uint_as_float((uint32_t)pi[27] | ((uint32_t)(pi[28] + 1) << 16)));
+    if (uvrec) {
+        uvrec[(size_t)i * 2 + 0] = make_float4(p[18], p[19], p[21], p[22]);
+        uvrec[(size_t)i * 2 + 1] = make_float4(p[24], p[25], 0.f, 0.f);
+    }
+}
+
 }  // namespace
 
 void free_bvh8(Bvh8& b) {
@@ -719,9 +745,19 @@ int build_bvh8(cudaStream_t stream, const DsrtTriangle* d_tris, int n, bool want
     max_nodes = (size_t)n / 2 + 2;
     DSRT_CUDA(cudaMalloc(&B.nodes, sizeof(uint4) * kNodeWords * max_nodes));
     DSRT_CUDA(cudaMalloc(&B.tri_records, sizeof(float4) * kTriWords * (size_t)n));
-    DSRT_CUDA(cudaMalloc(&B.shade_records, sizeof(float4) * 3 * (size_t)n));
+    {
+        // one-word shading records when every triangle has a single normal (always, with the reference's loader)
+        uint32_t nonflat = 0u;
+        DSRT_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t), stream));
+        k_check_flat_normals<<<nb, TB, 0, stream>>>(d_tris, n, counters);
+        DSRT_CUDA(cudaMemcpyAsync(&nonflat, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        DSRT_CUDA(cudaStreamSynchronize(stream));
+        B.shade_compact = nonflat == 0u && getenv("DSRT_FULL_SHADE_RECORDS") == nullptr;
+    }
+    DSRT_CUDA(cudaMalloc(&B.shade_records, sizeof(float4) * (B.shade_compact ? 1 : 3) * (size_t)n));
     if (want_uv) DSRT_CUDA(cudaMalloc(&B.uv_records, sizeof(float4) * 2 * (size_t)n));
-    k_shade_records<<<nb, TB, 0, stream>>>(d_tris, n, B.shade_records, B.uv_records);
+    if (B.shade_compact) k_shade_records_compact<<<nb, TB, 0, stream>>>(d_tris, n, B.shade_records, B.uv_records);
+    else k_shade_records<<<nb, TB, 0, stream>>>(d_tris, n, B.shade_records, B.uv_records);
 
     {
         float ext = 0.f;

@@ -12,7 +12,10 @@ namespace dsrt {
 struct Bvh8 {
     uint4* nodes = nullptr;          // num_nodes x 6 words (96 B each), breadth-first
     float4* tri_records = nullptr;   // num_tris x 3 words (48 B each), leaf order
-    float4* shade_records = nullptr; // num_tris x 3 words, indexed by uploaded triangle index
+    float4* shade_records = nullptr; // by uploaded triangle index: 3 words per triangle (n0 + material, n1 + texture, n2), or ONE
+                                     // word (n + material | (texture + 1) << 16) when shade_compact
+    bool shade_compact = false;      // every triangle has n0 == n1 == n2 (the reference's loader only makes flat normals,
+                                     // triangle.h:70-73) and ids below 65535: 16-byte records instead of 48
     float4* uv_records = nullptr;    // num_tris x 2 words, only when textures are present
     int num_nodes = 0;
     int num_tris = 0;

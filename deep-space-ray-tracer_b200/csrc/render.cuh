@@ -29,7 +29,8 @@ struct FrameConst {
     // scene
     const uint4* nodes;
     const float4* tri_records;
-    const float4* shade_records;
+    const float4* shade_records;      // 3 words per triangle, or 1 when shade_compact (bvh_build.h)
+    int shade_compact;
     const float4* uv_records;
     const float4* materials;          // DsrtMaterial as 3 x float4
     const DsrtTextureHeader* textures;

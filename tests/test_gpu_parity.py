@@ -227,6 +227,30 @@ def test_philox_frames_vs_oracle_across_views(dsrt, poses, ctx, oracle_scene10k,
     assert (limg == lrgb).all(2).mean() >= 0.995, (limg != lrgb).any(2).sum()
 
 
+def test_per_vertex_normals_take_the_full_shading_records(dsrt, poses):
+    """The reference's loader only makes flat normals (triangle.h:70-73), for which the library keeps
+    one-word shading records; GPUTriangle still carries three normals, and a scene whose normals
+    differ per vertex must shade through the interpolation w*n0 + u*n1 + v*n2 (gpu_render.cu:365-369)
+    like the oracle does.  Both record layouts against the oracle, LCG replay and Philox."""
+    rng = np.random.default_rng(9)
+    tris, mats = dsrt.synth_mesh(4000)
+    smooth = tris.copy()
+    for name in ("n1", "n2"):
+        for ax in "xyz":
+            smooth[name][ax] = (smooth[name][ax] + 0.35 * rng.standard_normal(len(smooth))).astype(np.float32)
+    w, h, spp = 96, 54, 8
+    _, sun, cam = pose_cam(dsrt, poses, 70, w, h, spp, DEPTH)
+    with dsrt.Context(0) as c:
+        for mesh in (tris, smooth):
+            c.upload_scene(mesh, mats)
+            sc = oracle.Scene(mesh, mats)
+            for mode, orng in ((dsrt.RNG_REF_LCG, 1), (dsrt.RNG_PHILOX, 0)):
+                c.render(cam, sun, dsrt.make_params(w, h, spp, DEPTH, mode))
+                img = c.readback_rgb8(spp, 2.0)
+                _, orgb, _ = sc.render(cam12_of(cam), w, h, spp, DEPTH, sun, rng_mode=orng)
+                assert (img == orgb).all(2).mean() >= 0.99, (mode, (img != orgb).any(2).sum())
+
+
 def test_builders_on_duplicate_and_degenerate_triangles(dsrt):
     """Coincident triangles (identical Morton keys), zero-area and needle triangles: both builders
     must produce a valid wide BVH and the same hits as the oracle."""
