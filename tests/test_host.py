@@ -193,3 +193,33 @@ def test_box_screen_bounds_are_conservative(dsrt, poses):
         assert vis.any()
         assert (px[vis] >= x0).all() and (px[vis] <= x1).all() and (py[vis] >= y0).all() and (py[vis] <= y1).all()
     assert bounded >= 4
+
+
+def test_cli_host_side_without_a_gpu(dsrt, tmp_path):
+    """The ray_tracer CLI up to the point where it needs the device: the reference's flags and
+    banner (src/main.cpp:194-215, 319-357), unknown flags ignored, the output directory emptied
+    (:41-50), poses parsed and transformed in double precision -- and, with no CUDA device, a loud
+    failure instead of any CPU rendering.  (On a GPU box the same command simply renders.)"""
+    import subprocess
+    import torch
+    exe = ROOT / "deep-space-ray-tracer_b200" / "ray_tracer"
+    if not exe.exists():
+        pytest.skip("ray_tracer not built")
+    out = tmp_path / "frames"
+    out.mkdir()
+    (out / "stale.txt").write_text("left over from an earlier run")
+    r = subprocess.run([str(exe), "--input_txt", str(POSE_FILE), "--output_dir", str(out), "--synthetic_tris", "500",
+                        "--frames", "0:3", "--width", "64", "--height", "36", "--spp", "2", "--max_depth", "3",
+                        "--some_unknown_flag", "7"], capture_output=True, text=True, timeout=120)
+    assert "Using output_dir: " + str(out) in r.stdout
+    assert "Loaded 99 poses." in r.stdout
+    assert r.stdout.count("=== Frame ") == 3
+    assert "sep(cam, model) = 1786.97 m" in r.stdout                      # SURVEY appendix B, frame 0
+    assert "sun_dir_model   = (0.327805, -0.756422, 0.566012)" in r.stdout
+    assert not (out / "stale.txt").exists()
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and (out / "frame_0000.ppm").exists() and (out / "frame_0002.png").exists()
+    else:
+        assert r.returncode != 0
+        assert "no usable CUDA device" in r.stderr and "no CPU path" in r.stderr
+        assert list(out.iterdir()) == []
