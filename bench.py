@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the render hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode frame|sample]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode frame|sample] [--config c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step is one pass of the hot path over one frame of BASELINE.json's config 2: pose 0 of the
@@ -11,18 +11,28 @@ sun with shadow rays.  Metric: Mrays/s (primary + bounce + shadow rays traced / 
   value      scene resident in HBM, CUDA events on the ctx stream around each step, L2
              flushed between steps, max over ranks
   e2e        the same frames through the C ABI with host buffers: camera/sun/params passed
-             from host memory, tone-mapped RGB8 frame read back to host every step
+             from host memory, tone-mapped RGB8 frame copied to page-locked host memory every
+             step, frames pipelined over two frame slots (dsrt_render_frame_async) the way the
+             CLI drives a pose sequence; the one-frame-at-a-time figure is beside it
   roofline   BVH traversal kernels (k_primary + k_trace share one traversal loop): algorithmic
-             bytes B(N) x rays / their summed launch durations (CUDA events on the ctx stream),
-             against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's CPU camera/bvh_node path (oracle/_ref/libref_cpu.so) on the
-             host cores, on a bounded sample of the same frame (rank 0, N = 1 only)
+             bytes B(N) x TRAVERSED rays / their summed launch durations (CUDA events on the ctx
+             stream), against MEASURED_PEAKS.json hbm_gbs; camera rays ended by tile culling
+             without a traversal are not charged
+  cpu_baseline  the reference's CPU camera/bvh_node path (oracle/_ref/libref_cpu.so) on the host
+             cores on BASELINE config 1 (10k triangles, 400x225, 16 spp, depth 10, whole frame)
+  c5         (N = 1) sub-record: BASELINE config 5 (10M triangles, diffuse, depth 16, 256 spp),
+             the configuration that does not fit L2, with its own roofline
+  c4_sample  (N > 1) sub-record: BASELINE config 4 (3840x2160, 1000 spp) sample-sharded over the
+             ranks with one NCCL sum-reduce of the float accumulation buffer, reduce timed
 
 N > 1: frame-parallel -- every rank renders its own frame of the same configuration (pose 0) per
-step, no collective (scaling "weak": per-GPU work fixed, N frames per step).  --poses sequence
-walks the pose file instead (rank r renders pose step*N + r; later poses are closer to the station
-and cost more, so steps are then not comparable across N).  --mode sample shards ONE frame's samples over the
-ranks and sums the float accumulation buffers with one NCCL reduce ("strong").
+step, no collective (scaling "weak": per-GPU work fixed, N frames per step).  --mode sample shards
+ONE frame's samples over the ranks and sums the float accumulation buffers with one NCCL reduce
+("strong").  --config c3 renders the 99-pose sequence (1080p, 250 spp, depth 50) frame-parallel with
+PPM + PNG written and reports frames/s.
+
+Only the baseline legs (cpu_baseline, ref_gpu_kernel, run_reference) touch oracle/; the timed product
+path never does (tests/test_host.py checks this file's imports).
 """
 from __future__ import annotations
 
@@ -30,8 +40,10 @@ import argparse
 import json
 import math
 import os
+import queue
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -124,38 +136,48 @@ def parse_args():
     ap.add_argument("--diffuse_only", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
-    ap.add_argument("--cpu_step", type=int, default=4, help="pixel stride of the CPU sample")
+    ap.add_argument("--no_sub", action="store_true", help="skip the c5 (N = 1) / c4_sample (N > 1) sub-records")
+    ap.add_argument("--cpu_step", type=int, default=4, help="pixel stride of the CPU sample of the reference arm")
     ap.add_argument("--spb", type=int, default=0, help="samples of a pixel in flight together (0 = library default)")
-    ap.add_argument("--config", default="", choices=["", "c2", "c4", "c5"],
-                    help="BASELINE.json presets: c2 = the default; c4 = 3840x2160, 1000 spp (use with --mode sample); "
-                         "c5 = 10M triangles, diffuse only, depth 16, 1080p, 256 spp")
+    ap.add_argument("--config", default="", choices=["", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json presets: c2 = the default; c3 = the 99-pose sequence at 1080p, 250 spp, depth 50, frames "
+                         "written (frames/s); c4 = 3840x2160, 1000 spp (use with --mode sample); c5 = 10M triangles, diffuse only, "
+                         "depth 16, 1080p, 256 spp")
     ap.add_argument("--no_ref_gpu", action="store_true", help="skip timing the reference's own GPU kernel beside the result")
-    ap.add_argument("--poses", default="fixed", choices=["fixed", "sequence"],
-                    help="frame-parallel runs: every rank renders pose 0 (fixed, the default) or rank r renders pose step*N + r")
+    ap.add_argument("--no_write", action="store_true", help="c3: render and read back but do not write the frames")
     a = ap.parse_args()
     if a.config == "c4":
         a.width, a.height, a.spp = 3840, 2160, 1000
     elif a.config == "c5":
         a.tris, a.diffuse_only, a.depth, a.spp = 10_000_000, True, 16, 256
+    elif a.config == "c3":
+        a.width, a.height, a.spp, a.depth = 1920, 1080, 250, 50
     return a
 
 
-def workload_name(a):
-    return (f"pose 0 of rendezvous_1s_dt0_01s.txt, synthetic {a.tris}-triangle station"
-            f"{' (diffuse only)' if a.diffuse_only else ''}, {a.width}x{a.height}, {a.spp} spp, depth {a.depth}, "
+def workload_name(tris, diffuse_only, width, height, spp, depth, what="pose 0"):
+    return (f"{what} of rendezvous_1s_dt0_01s.txt, synthetic {tris}-triangle station"
+            f"{' (diffuse only)' if diffuse_only else ''}, {width}x{height}, {spp} spp, depth {depth}, "
             "directional sun + shadow rays")
+
+
+def env_overrides():
+    """Tuning switches of the library that are set in the environment change what is measured: say so."""
+    return {k: v for k, v in os.environ.items() if k.startswith("DSRT_")}
 
 
 # --------------------------------------------------------------------------------------------
 def run_reference(a, rank, world):
-    """The reference's own CPU implementation of the path on the host cores."""
+    """The reference's own CPU implementation of the path on the host cores.  Mesh, poses and camera
+    come from oracle-side helpers: this arm never loads the product's library."""
     if rank != 0:
         return
-    import dsrt_b200 as d          # host helpers only (mesh, pose); no GPU call is made here
+    import oracle
     import refcpu
-    poses = d.read_pose_file(POSE_FILE)
-    cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
-    tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
+    import synthmesh
+    poses = oracle.read_pose_file(POSE_FILE)
+    cam_pos, sun, _ = oracle.pose_to_model_frame(poses[0])
+    tris, mats = synthmesh.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
     step = max(1, a.cpu_step)
     sample = (f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, 1 of {a.spp} samples per step "
               f"(sample index = step), all {a.depth} bounces")
@@ -170,14 +192,12 @@ def run_reference(a, rank, world):
                              s_begin=i % a.spp, s_end=i % a.spp + 1, threads=cores)
             return s, int(c.sum())
     else:
-        import oracle
         kind = "port"
         t0 = time.perf_counter()
         sc = oracle.Scene(tris, mats)
         build_s = time.perf_counter() - t0
         cores = os.cpu_count() or 1
-        cam = d.camera_look_at_origin(cam_pos, 40.0, a.width // step, a.height // step)
-        cam12 = np.array(cam.origin.tuple() + cam.lower_left_corner.tuple() + cam.horizontal.tuple() + cam.vertical.tuple(), np.float32)
+        cam12, _ = oracle.camera_init(cam_pos, 40.0, a.width // step, a.height // step)
 
         def one(i):
             t0 = time.perf_counter()
@@ -196,7 +216,8 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": "Mrays/s (primary+bounce+shadow)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample, "bvh_build_s": build_s},
+        "config": {"workload": workload_name(a.tris, a.diffuse_only, a.width, a.height, a.spp, a.depth), "sample": sample,
+                   "bvh_build_s": build_s},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,6 +226,58 @@ def run_reference(a, rank, world):
 
 
 # --------------------------------------------------------------------------------------------
+class Timed:
+    """Sums of one timed loop."""
+
+    def __init__(self):
+        self.ms = self.rays = self.launches = self.ext_ms = self.prim_ms = self.shade_ms = self.culled = 0.0
+        self.reduce_ms = 0.0
+
+
+def roofline_record(tris, t: Timed, steps, world, traffic=None, l2_read=None):
+    """achieved = algorithmic bytes of the rays that were TRAVERSED / the live time of the traversal kernels."""
+    peak, peak_kind = measured_peak_gbs()
+    bpr = algorithmic_bytes_per_ray(tris)
+    rays = t.rays / world                      # per rank (ext_ms is the per-rank average)
+    trav = rays - t.culled
+    achieved = trav * bpr / (t.ext_ms * 1e-3) / 1e9 if t.ext_ms > 0 else 0.0
+    all_rays = rays * bpr / (t.ext_ms * 1e-3) / 1e9 if t.ext_ms > 0 else 0.0
+    in_l2 = tris <= 2_000_000
+    note = ("the scene (57 MB of nodes and records at 1M triangles) is L2-resident: the traversal is bound by instruction issue and "
+            "L1/L2 latency, not by HBM; `achieved` counts SURVEY 8(d)'s algorithmic bytes of the traversed rays, most of which the "
+            "caches serve (`traffic` is what DRAM really moved)" if in_l2 else
+            "the scene (about 0.6 GB of nodes and records at 10M triangles) does not fit L2: traversal is bound by DRAM/L2 latency "
+            "under incoherent access; `traffic` is what DRAM really moved")
+    return {"bound": "issue/L2" if in_l2 else "hbm", "kernel": "k_primary + k_trace (BVH8 traversal, closest and any hit)",
+            "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+            "frac_all_rays": all_rays / peak,
+            "bytes_per_ray": bpr, "rays_per_step": rays / steps, "traversed_rays_per_step": trav / steps,
+            # camera rays whose 8x4-pixel tile provably sees no triangle end as misses without a traversal; they count
+            # in the headline Mrays/s (every path of the frame is resolved) but not here
+            "culled_primary_rays_per_step": t.culled / steps,
+            "traversed_mrays_per_s": (trav / (t.ext_ms * 1e-3) / 1e6) if t.ext_ms else None,
+            "kernel_ms_per_step": t.ext_ms / steps, "k_primary_ms_per_step": t.prim_ms / steps,
+            "k_shade_ms_per_step": t.shade_ms / steps, "traffic": traffic,
+            "traffic_gbs": (traffic / (t.ext_ms / steps * 1e-3) / 1e9) if traffic and t.ext_ms else None,
+            "traffic_frac_of_peak": (traffic / (t.ext_ms / steps * 1e-3) / 1e9 / peak) if traffic and t.ext_ms else None,
+            "l2_to_sm_read_gbs": (l2_read / (t.ext_ms / steps * 1e-3) / 1e9) if l2_read and t.ext_ms else None,
+            "note": note}
+
+
+def committed_traffic(name, workload):
+    """DRAM bytes of the traversal launches of one step from the committed `ncu --set full` capture of this same
+    workload (profiles/<name>); null for other workloads."""
+    prof = ROOT / "profiles" / name
+    if prof.exists():
+        try:
+            pj = json.loads(prof.read_text())
+            if pj.get("workload") == workload:
+                return pj.get("dram_bytes_per_step"), pj.get("l2_to_sm_read_bytes_per_step")
+        except Exception:  # noqa: BLE001
+            pass
+    return None, None
+
+
 def run_dsrt(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -219,6 +292,9 @@ def run_dsrt(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     poses = d.read_pose_file(POSE_FILE)
+    if a.config == "c3":
+        run_sequence(a, rank, world, local_rank, torch, dist, d, sharding, dev, poses)
+        return
     tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
     import hashlib
     mesh_sha = hashlib.sha256(np.ascontiguousarray(np.stack([np.stack([tris[v][k] for k in "xyz"], 1) for v in ("v0", "v1", "v2")], 1)).tobytes()).hexdigest()
@@ -229,22 +305,11 @@ def run_dsrt(a, rank, world, local_rank):
     if a.spb > 0:
         ctx.set_samples_per_batch(a.spb)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    params = d.make_params(a.width, a.height, a.spp, a.depth, d.RNG_PHILOX)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    # the e2e leg reads every frame back into page-locked host memory (the caller's buffer; any host pointer works)
-    rgb = torch.empty((a.height, a.width, 3), dtype=torch.uint8, pin_memory=True).numpy()
 
-    def frame_inputs(i):
-        # frame-parallel: step i covers frames i*world .. i*world+world-1, rank r takes its own
-        idx = 0
-        if world > 1 and a.mode == "frame" and a.poses == "sequence":
-            idx = (sharding.frames_of_rank((i + 1) * world, rank, world)[i]) % len(poses)
-        cam_pos, sun, _ = d.pose_to_model_frame(poses[idx])
-        return d.camera_look_at_origin(cam_pos, 40.0, a.width, a.height, a.spp, a.depth), sun
-
-    s_lo, s_hi = 0, a.spp
-    if world > 1 and a.mode == "sample":
-        s_lo, s_hi = sharding.sample_range(a.spp, rank, world)
+    def frame_inputs(width, height, spp, depth):
+        cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+        return d.camera_look_at_origin(cam_pos, 40.0, width, height, spp, depth), sun
 
     def reduce_accum():
         # one NCCL sum-reduce of the float accumulation buffer to rank 0 (NVLink/NVSwitch)
@@ -254,180 +319,389 @@ def run_dsrt(a, rank, world, local_rank):
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
         sharding.reduce_accum(torch.as_tensor(_P(), device=dev), dst=0)
 
-    def step(i, timed):
-        cam, sun = frame_inputs(i)
-        flush.fill_(i & 0xFF)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        fs = ctx.render(cam, sun, params, sample_begin=s_lo, sample_end=s_hi)
-        if world > 1 and a.mode == "sample":
-            with torch.cuda.stream(stream):
-                reduce_accum()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1), fs
+    def timed_loop(width, height, spp, depth, steps, warmup, sample_mode):
+        """Device-timed steps: CUDA events on the ctx stream, L2 flushed before each, barrier + synchronize around."""
+        params = d.make_params(width, height, spp, depth, d.RNG_PHILOX)
+        cam, sun = frame_inputs(width, height, spp, depth)
+        s_lo, s_hi = (sharding.sample_range(spp, rank, world) if (world > 1 and sample_mode) else (0, spp))
+        t = Timed()
 
-    for i in range(a.warmup):
-        step(i, False)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms = rays = launches = ext_ms = ext_rays = prim_ms = shade_ms = culled = 0.0
-    for i in range(a.steps):
-        m, fs = step(a.warmup + i, True)
-        ms += m
-        rays += fs.rays
-        launches += fs.kernel_launches
-        ext_ms += fs.extend_ms
-        prim_ms += fs.primary_ms
-        shade_ms += fs.shade_ms
-        ext_rays += fs.rays
-        culled += fs.culled_primary_rays
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    clk = clocks.stop()
+        def step(i):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize(dev)
+            e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            fs = ctx.render(cam, sun, params, sample_begin=s_lo, sample_end=s_hi)
+            em.record(stream)
+            if world > 1 and sample_mode:
+                with torch.cuda.stream(stream):
+                    reduce_accum()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1), em.elapsed_time(e1), fs
+
+        for i in range(warmup):
+            step(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        for i in range(steps):
+            m, r, fs = step(warmup + i)
+            t.ms += m
+            t.reduce_ms += r
+            t.rays += fs.rays
+            t.launches += fs.kernel_launches
+            t.ext_ms += fs.extend_ms
+            t.prim_ms += fs.primary_ms
+            t.shade_ms += fs.shade_ms
+            t.culled += fs.culled_primary_rays
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop()
+        if world > 1:
+            mx = torch.tensor([t.ms, t.reduce_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            t.ms, t.reduce_ms = mx.tolist()
+            sm = torch.tensor([t.rays, t.launches, t.ext_ms, t.prim_ms, t.shade_ms, t.culled], dtype=torch.float64, device=dev)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            t.rays, t.launches, t.ext_ms, t.prim_ms, t.shade_ms, t.culled = sm.tolist()
+            t.ext_ms /= world            # average per-rank time of the traversal kernels
+            t.prim_ms /= world
+            t.shade_ms /= world
+            t.culled /= world
+        return t, clk, params, cam, sun, (s_lo, s_hi)
+
+    sample_mode = a.mode == "sample"
+    t, clk, params, cam, sun, (s_lo, s_hi) = timed_loop(a.width, a.height, a.spp, a.depth, a.steps, a.warmup, sample_mode)
 
     # ---- end to end through the C ABI with host buffers (render + tone-map + D2H each step)
-    e2e_ms = e2e_rays = 0.0
+    e2e_ms = e2e_rays = e2e_sync_ms = 0.0
     if not a.no_e2e:
+        rgbs = [torch.empty((a.height, a.width, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+        # (1) one frame at a time: render, then tone map + copy, each waited for
         for i in range(a.steps):
-            cam, sun = frame_inputs(a.warmup + i)
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             fs = ctx.render(cam, sun, params, sample_begin=s_lo, sample_end=s_hi)
-            if world > 1 and a.mode == "sample":
+            if world > 1 and sample_mode:
                 with torch.cuda.stream(stream):
                     reduce_accum()
                 torch.cuda.synchronize(dev)
-            if not (world > 1 and a.mode == "sample" and rank != 0):
-                ctx.readback_rgb8(a.spp, params.gamma, rgb)
-            e2e_ms += 1e3 * (time.perf_counter() - t0)
-            e2e_rays += fs.rays
+            if not (world > 1 and sample_mode and rank != 0):
+                ctx.readback_rgb8(a.spp, params.gamma, rgbs[0])
+            e2e_sync_ms += 1e3 * (time.perf_counter() - t0)
+        # (2) the way a pose sequence is driven: two frames in flight on two frame slots, every frame's camera and sun
+        # passed from host memory and its RGB8 image copied to page-locked host memory inside the timed region
+        if world > 1 and sample_mode:
+            e2e_ms, e2e_rays = e2e_sync_ms, t.rays / max(world, 1)
+        else:
+            for k in range(2):             # warm both slots (work memory of slot 1 is allocated at first use)
+                ctx.render_async(k, cam, sun, params)
+                ctx.readback_rgb8_async(k, a.spp, params.gamma, rgbs[k])
+            for k in range(2):
+                ctx.frame_wait(k)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for i in range(a.steps):
+                k = i & 1
+                if i >= 2:
+                    e2e_rays += ctx.frame_wait(k).rays
+                cam_i, sun_i = frame_inputs(a.width, a.height, a.spp, a.depth)        # host-side pose transform + camera, per frame
+                ctx.render_async(k, cam_i, sun_i, params)
+                ctx.readback_rgb8_async(k, a.spp, params.gamma, rgbs[k])
+            for i in range(max(0, a.steps - 2), a.steps):
+                e2e_rays += ctx.frame_wait(i & 1).rays
+            e2e_ms = 1e3 * (time.perf_counter() - t0)
 
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
-        s = torch.tensor([rays, e2e_rays, launches, ext_ms, ext_rays], dtype=torch.float64, device=dev)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        rays, e2e_rays, launches, ext_ms, ext_rays = s.tolist()
-        ext_ms /= world            # average per-rank time of the traversal kernel
+        mx = torch.tensor([e2e_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        e2e_ms, e2e_sync_ms = mx.tolist()
+        sm = torch.tensor([e2e_rays], dtype=torch.float64, device=dev)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_rays = sm.tolist()[0]
 
+    # ---- sub-records
+    sub = {}
+    if not a.no_sub and a.config in ("", "c2"):
+        if world > 1:
+            # BASELINE config 4: one 3840x2160 frame at 1000 spp, samples sharded over the ranks, one NCCL reduce
+            t4, clk4, _, _, _, _ = timed_loop(3840, 2160, 1000, a.depth, 3, 1, True)
+            # the reduce alone, all ranks entering together (the figure inside the step also holds the wait for the slowest rank)
+            alone = []
+            for _ in range(3):
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                with torch.cuda.stream(stream):
+                    reduce_accum()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                alone.append(e0.elapsed_time(e1))
+            ar = torch.tensor([min(alone)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+            sub["c4_sample"] = {
+                "workload": workload_name(a.tris, a.diffuse_only, 3840, 2160, 1000, a.depth),
+                "parallelism": f"sample-parallel x{world}: rank r renders global samples [1000 r/{world}, 1000 (r+1)/{world}), "
+                               "one NCCL sum-reduce of the float accumulation buffer to rank 0",
+                "steps": 3, "warmup": 1, "ms_per_frame": t4.ms / 3, "value": t4.rays / (t4.ms * 1e3), "unit": "Mrays/s",
+                "scaling": "strong", "reduce_bytes": 3840 * 2160 * 3 * 4,
+                "reduce_ms_in_step": t4.reduce_ms / 3, "reduce_ms_alone": ar.tolist()[0],
+                "reduce_alone_gbs": 3840 * 2160 * 3 * 4 / (ar.tolist()[0] * 1e-3) / 1e9,
+                "clocks": clk4}
     if rank == 0:
-        peak, peak_kind = measured_peak_gbs()
-        bpr = algorithmic_bytes_per_ray(a.tris)
-        achieved = (ext_rays / world) * bpr / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        traffic = l2_read = None
-        # DRAM bytes of the traversal launches of one step, from the committed `ncu --set full`
-        # capture of this same workload (profiles/trace_ncu_summary.json); null for other workloads
-        prof = ROOT / "profiles" / "trace_ncu_summary.json"
-        if prof.exists():
-            try:
-                pj = json.loads(prof.read_text())
-                if pj.get("workload") == workload_name(a):
-                    traffic = pj.get("dram_bytes_per_step")
-                    l2_read = pj.get("l2_to_sm_read_bytes_per_step")
-            except Exception:  # noqa: BLE001
-                traffic = None
+        wl = workload_name(a.tris, a.diffuse_only, a.width, a.height, a.spp, a.depth)
+        traffic, l2_read = committed_traffic("trace_ncu_summary.json", wl)
+        if traffic is None:
+            traffic, l2_read = committed_traffic("trace_ncu_summary_c5.json", wl)
         out = {
-            "metric": "Mrays/s (primary+bounce+shadow)", "value": rays / (ms * 1e3), "unit": "Mrays/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-            "higher_is_better": True, "scaling": "strong" if (world > 1 and a.mode == "sample") else "weak",
+            "metric": "Mrays/s (primary+bounce+shadow)", "value": t.rays / (t.ms * 1e3), "unit": "Mrays/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t.ms / a.steps,
+            "higher_is_better": True, "scaling": "strong" if (world > 1 and sample_mode) else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": f"{a.mode}-parallel x{world}" if world > 1 else "single GPU",
+            "config": {"workload": wl, "parallelism": f"{a.mode}-parallel x{world}" if world > 1 else "single GPU",
                        "rng": "philox4x32-10", "l2": "flushed between steps (256 MiB write)",
-                       "frames_per_s": world * a.steps / (ms * 1e-3) if a.mode == "frame" else a.steps / (ms * 1e-3),
+                       "frames_per_s": world * a.steps / (t.ms * 1e-3) if a.mode == "frame" else a.steps / (t.ms * 1e-3),
                        # SURVEY 8(d): generator parameters and a SHA-256 of the vertex buffer go with every number
                        "mesh": {"generator": "dsrt_synth_mesh", "seed": 1337, "triangles": int(a.tris), "diffuse_only": bool(a.diffuse_only),
                                 "vertices_sha256": mesh_sha},
                        "bvh": {"wide_nodes": st.num_wide_nodes, "levels": st.num_levels, "build_ms": st.build_ms,
                                "build_ms_first_call": st_first.build_ms, "upload_ms": st.upload_ms, "sah": st.sah_cost,
-                               "builder": os.environ.get("DSRT_BVH_BUILDER", "ploc")}},
+                               "builder": os.environ.get("DSRT_BVH_BUILDER", "ploc")},
+                       "env_overrides": env_overrides()},
             "clocks": clk,
             "e2e": {"value": (e2e_rays / (e2e_ms * 1e3)) if e2e_ms else None, "unit": "Mrays/s",
                     "h2d_bytes_per_step": 104 + 48 + 24 + 8, "d2h_bytes_per_step": a.width * a.height * 3,
-                    "ms_per_step": e2e_ms / a.steps if e2e_ms else None},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_primary + k_trace (BVH8 traversal, closest and any hit)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                         "bytes_per_ray": bpr, "rays_per_step": ext_rays / world / a.steps,
-                         "kernel_ms_per_step": ext_ms / a.steps, "k_primary_ms_per_step": prim_ms / a.steps,
-                         "k_shade_ms_per_step": shade_ms / a.steps, "traffic": traffic,
-                         # of rays_per_step (rank 0's steps): camera rays whose 8x4-pixel tile provably sees no triangle
-                         # and that ended as misses without a traversal; the rest were traversed
-                         "culled_primary_rays_per_step": culled / a.steps,
-                         "traversed_mrays_per_s": ((ext_rays / world - culled) / (ext_ms * 1e-3) / 1e6) if ext_ms else None,
-                         # what actually moved, next to the algorithmic figure: DRAM and L2->SM bytes of the same launches
-                         # (ncu, profiles/trace_ncu_summary.json) over the live kernel time
-                         "traffic_gbs": (traffic / (ext_ms / a.steps * 1e-3) / 1e9) if traffic and ext_ms else None,
-                         "l2_to_sm_read_gbs": (l2_read / (ext_ms / a.steps * 1e-3) / 1e9) if l2_read and ext_ms else None,
-                         "note": "the 1M-triangle scene (57 MB of nodes and records) is L2-resident, so the traversal is bound by "
-                                 "instruction issue / the ALU pipe, not by HBM (profiles/r01_be_trace_ncu.txt: issue 60-75 %, ALU 50-56 %); "
-                                 "achieved counts SURVEY 8(d)'s algorithmic bytes, most of which the caches serve"},
+                    "ms_per_step": e2e_ms / a.steps if e2e_ms else None,
+                    "how": "two frames in flight on two frame slots (dsrt_render_frame_async + dsrt_readback_rgb8_async into page-locked "
+                           "host buffers + dsrt_frame_wait), wall clock over all steps",
+                    "ms_per_step_one_at_a_time": e2e_sync_ms / a.steps if e2e_sync_ms else None},
+            "gpu_launches": int(t.launches),
+            "roofline": roofline_record(a.tris, t, a.steps, world, traffic, l2_read),
         }
-        if world == 1 and not a.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(a, tris, mats, poses)
-        if world == 1 and not a.no_ref_gpu and a.tris <= 2_000_000:
-            ctx.close()
-            out["ref_gpu_kernel"] = ref_gpu_kernel(a, tris, mats, poses, rays / a.steps)
-        print(json.dumps(out), flush=True)
+        if world > 1 and sample_mode:
+            out["reduce_ms_per_step"] = t.reduce_ms / a.steps
+        out.update(sub)
     ctx.close()
+    del flush
+    if rank == 0:
+        if world == 1 and not a.no_sub and a.config in ("", "c2"):
+            out["c5"] = c5_record(torch, dev, d)
+        if world == 1 and not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not a.no_ref_gpu and a.tris <= 2_000_000:
+            out["ref_gpu_kernel"] = ref_gpu_kernel(a, t.rays / a.steps, (t.rays - t.culled) / a.steps)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def ref_gpu_kernel(a, tris, mats, poses, rays_per_frame):
+def c5_record(torch, dev, d):
+    """BASELINE config 5 on this GPU: 10M triangles, diffuse only, depth 16, 1080p, 256 spp -- the scene that does not
+    fit the 126 MB L2 (about 0.6 GB of nodes and triangle records)."""
+    tris_n, w, h, spp, depth, steps, warmup = 10_000_000, 1920, 1080, 256, 16, 5, 2
+    try:
+        poses = d.read_pose_file(POSE_FILE)
+        cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+        cam = d.camera_look_at_origin(cam_pos, 40.0, w, h, spp, depth)
+        tris, mats = d.synth_mesh(tris_n, diffuse_only=True)
+        ctx = d.Context(dev.index)
+        st = ctx.upload_scene(tris, mats)
+        del tris
+        ctx.set_stage_timing(True)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        params = d.make_params(w, h, spp, depth, d.RNG_PHILOX)
+        t = Timed()
+        for i in range(warmup + steps):
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fs = ctx.render(cam, sun, params)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            if i < warmup:
+                continue
+            t.ms += e0.elapsed_time(e1)
+            t.rays += fs.rays
+            t.launches += fs.kernel_launches
+            t.ext_ms += fs.extend_ms
+            t.prim_ms += fs.primary_ms
+            t.shade_ms += fs.shade_ms
+            t.culled += fs.culled_primary_rays
+        ctx.close()
+        wl = workload_name(tris_n, True, w, h, spp, depth)
+        traffic, l2_read = committed_traffic("trace_ncu_summary_c5.json", wl)
+        return {"workload": wl, "steps": steps, "warmup": warmup, "ms_per_step": t.ms / steps, "value": t.rays / (t.ms * 1e3),
+                "unit": "Mrays/s", "l2": "not flushed: the scene and the 19 GB of work memory of a step are far larger than L2",
+                "bvh": {"wide_nodes": st.num_wide_nodes, "levels": st.num_levels, "build_ms": st.build_ms, "sah": st.sah_cost},
+                "gpu_launches": int(t.launches), "roofline": roofline_record(tris_n, t, steps, 1, traffic, l2_read)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def run_sequence(a, rank, world, local_rank, torch, dist, d, sharding, dev, poses):
+    """BASELINE config 3: the whole pose sequence (99 poses), 1080p, 250 spp, depth 50 (the reference's defaults),
+    frame-parallel: rank r renders poses r, r + N, ... with two frames in flight, PPM + PNG of every frame written by
+    writer threads (what the reference's loop does per frame, src/main.cpp:310-431).  No collective.  The metric is
+    frames/s over the wall clock of the frame loop (scene upload and CUDA start-up are reported beside it)."""
+    t_start = time.perf_counter()
+    tris, mats = d.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
+    ctx = d.Context(local_rank)
+    st = ctx.upload_scene(tris, mats)
+    params = d.make_params(a.width, a.height, a.spp, a.depth, d.RNG_PHILOX)
+    mine = sharding.frames_of_rank(len(poses), rank, world)
+    outdir = Path(tempfile.mkdtemp(prefix=f"dsrt_c3_r{rank}_"))
+    bufs = queue.Queue()
+    for _ in range(4):
+        bufs.put(torch.empty((a.height, a.width, 3), dtype=torch.uint8, pin_memory=True).numpy())
+    jobs = queue.Queue()
+    written = []
+
+    def writer():
+        while True:
+            it = jobs.get()
+            if it is None:
+                return
+            idx, buf = it
+            if not a.no_write:
+                d.write_ppm(outdir / f"frame_{idx:04d}.ppm", buf, a.width, a.height)
+                d.write_png(outdir / f"frame_{idx:04d}.png", buf, a.width, a.height)
+            written.append(idx)
+            bufs.put(buf)
+
+    writers = [threading.Thread(target=writer) for _ in range(2)]
+    for w in writers:
+        w.start()
+
+    def enqueue(slot, idx):
+        cam_pos, sun, _ = d.pose_to_model_frame(poses[idx])
+        cam = d.camera_look_at_origin(cam_pos, 40.0, a.width, a.height, a.spp, a.depth)
+        buf = bufs.get()
+        ctx.render_async(slot, cam, sun, params)
+        ctx.readback_rgb8_async(slot, a.spp, params.gamma, buf)
+        return idx, buf
+
+    # warm-up: allocate both slots' work memory on the most expensive pose, outside the timed loop
+    for k in range(2):
+        _, buf = enqueue(k, len(poses) - 1)
+        ctx.frame_wait(k)
+        bufs.put(buf)
+    setup_s = time.perf_counter() - t_start
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    inflight = [None, None]
+    rays = dev_ms = 0.0
+    for n, idx in enumerate(mine):
+        k = n & 1
+        if inflight[k] is not None:
+            fs = ctx.frame_wait(k)
+            rays += fs.rays
+            dev_ms += fs.device_ms
+            jobs.put(inflight[k])
+        inflight[k] = enqueue(k, idx)
+    for k in ((len(mine) & 1), (len(mine) & 1) ^ 1):
+        if inflight[k] is not None:
+            fs = ctx.frame_wait(k)
+            rays += fs.rays
+            dev_ms += fs.device_ms
+            jobs.put(inflight[k])
+    for _ in writers:
+        jobs.put(None)
+    for w in writers:
+        w.join()
+    loop_s = time.perf_counter() - t0
+    ctx.close()
+    nbytes = sum(f.stat().st_size for f in outdir.iterdir())
+    for f in outdir.iterdir():
+        f.unlink()
+    outdir.rmdir()
+    if world > 1:
+        mx = torch.tensor([loop_s, setup_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        loop_s, setup_s = mx.tolist()
+        sm = torch.tensor([rays, dev_ms, float(len(written)), float(nbytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        rays, dev_ms, nwritten, nbytes = sm.tolist()
+    else:
+        nwritten = len(written)
+    if rank == 0:
+        out = {"metric": "frames/s (99-pose sequence, 1080p, 250 spp, depth 50, PPM + PNG written)", "value": nwritten / loop_s,
+               "unit": "frames/s", "n_gpus": world, "steps": int(nwritten), "warmup": 2, "ms_per_step": 1e3 * loop_s / max(nwritten, 1),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_name(a.tris, a.diffuse_only, a.width, a.height, a.spp, a.depth, "all 99 poses"),
+                          "parallelism": f"frame-parallel x{world}, rank r renders poses r, r+{world}, ...; two frames in flight per GPU; no collective",
+                          "frames_written": int(nwritten), "bytes_written": int(nbytes), "write": not a.no_write,
+                          "env_overrides": env_overrides()},
+               "sequence_wall_s": loop_s, "setup_s_max_over_ranks": setup_s, "sum_device_ms": dev_ms,
+               "mrays_per_s": rays / (loop_s * 1e6), "bvh_build_ms": st.build_ms,
+               "e2e": {"value": nwritten / loop_s, "unit": "frames/s", "h2d_bytes_per_step": 104 + 48 + 24 + 8,
+                       "d2h_bytes_per_step": a.width * a.height * 3},
+               "gpu_launches": None}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ref_gpu_kernel(a, rays_per_frame, traversed_per_frame):
     """The reference's own CUDA path on the same B200 and frame (its CPU BVH build + its
     megakernel, oracle/_ref/libref_gpu.so): reported beside the result, not part of it.  The
     reference does not count rays; Mrays/s uses this path's ray count for the same frame."""
     try:
-        import dsrt_b200 as d
+        import oracle
         import refgpu
+        import synthmesh
         if not refgpu.available():
             return {"value": None, "note": "oracle/_ref/libref_gpu.so not present"}
-        cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
+        poses = oracle.read_pose_file(POSE_FILE)
+        cam_pos, sun, _ = oracle.pose_to_model_frame(poses[0])
+        tris, mats = synthmesh.synth_mesh(a.tris, diffuse_only=a.diffuse_only)
         ref = refgpu.RefScene(tris, mats, cam_pos, sun, a.width, a.height, a.spp, a.depth)
         ms = [ref.render()[1] for _ in range(3)]
         build_ms = ref.build_ms
         ref.close()
         best = min(ms[1:])
         return {"value": rays_per_frame / (best * 1e3), "unit": "Mrays/s", "kernel_ms_per_frame": best,
+                "traversed_mrays_per_s": traversed_per_frame / (best * 1e3),
                 "scene_build_ms_per_frame": build_ms,
                 "note": "render_kernel of the unmodified reference (one thread per pixel, LCG), second and third of 3 frames; "
-                        "its build_gpu_scene (CPU BVH + uploads, redone for every frame by its main()) is timed separately"}
+                        "its build_gpu_scene (CPU BVH + uploads, redone for every frame by its main()) is timed separately; "
+                        "the apples-to-apples figure is the frame time ratio"}
     except Exception as e:  # noqa: BLE001
         return {"value": None, "note": repr(e)}
 
 
-def cpu_baseline(a, tris, mats, poses):
-    """The reference CPU path on a bounded sample of the same frame (rank 0, N = 1)."""
-    import dsrt_b200 as d
-    cam_pos, sun, _ = d.pose_to_model_frame(poses[0])
-    step = max(1, a.cpu_step)
+def cpu_baseline():
+    """The reference CPU path on BASELINE config 1: pose 0, the synthetic 10k-triangle
+    station, 400x225, 16 spp, depth 10, the WHOLE frame, all host cores."""
+    import oracle
+    import synthmesh
+    tris_n, w, h, spp, depth = 10_000, 400, 225, 16, 10
     cores = os.cpu_count() or 1
-    ns = min(8, a.spp)
-    sample = f"every {step}th pixel in x and y of the {a.width}x{a.height} frame, {ns} of {a.spp} samples, depth {a.depth}"
+    sample = f"BASELINE config 1, whole frame: {tris_n} triangles, {w}x{h}, {spp} spp, depth {depth}, pose 0"
     try:
+        poses = oracle.read_pose_file(POSE_FILE)
+        cam_pos, sun, _ = oracle.pose_to_model_frame(poses[0])
+        tris, mats = synthmesh.synth_mesh(tris_n)
         import refcpu
         if refcpu.available():
             sc = refcpu.RefCpuScene(tris, mats)
-            secs, c = sc.render(cam_pos, sun, a.width, a.height, a.spp, a.depth, step_x=step, step_y=step, s_begin=0, s_end=ns, threads=cores)
+            sc.render(cam_pos, sun, w, h, spp, depth, s_begin=0, s_end=1, threads=cores)        # warm the thread pool
+            secs, c = sc.render(cam_pos, sun, w, h, spp, depth, threads=cores)
             return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-                    "sample": sample, "bvh_build_s": sc.build_s, "seconds": secs}
-        import oracle
+                    "sample": sample, "bvh_build_s": sc.build_s, "seconds_per_frame": secs, "rays": int(c.sum())}
         sc = oracle.Scene(tris, mats)
-        w, h = a.width // step, a.height // step
-        cam = d.camera_look_at_origin(cam_pos, 40.0, w, h)
-        cam12 = np.array(cam.origin.tuple() + cam.lower_left_corner.tuple() + cam.horizontal.tuple() + cam.vertical.tuple(), np.float32)
+        cam12, _ = oracle.camera_init(cam_pos, 40.0, w, h)
         t0 = time.perf_counter()
-        _, _, c = sc.render(cam12, w, h, a.spp, a.depth, sun, rng_mode=1, s_begin=0, s_end=ns)
+        _, _, c = sc.render(cam12, w, h, spp, depth, sun, rng_mode=1)
         secs = time.perf_counter() - t0
         return {"value": float(c.sum()) / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                "sample": f"{w}x{h} down-sampled frame, {ns} of {a.spp} samples, depth {a.depth}", "seconds": secs}
+                "sample": sample, "seconds_per_frame": secs, "rays": int(c.sum())}
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
 

@@ -95,8 +95,9 @@ SYMBOLS = [
     "dsrt_create", "dsrt_destroy", "dsrt_last_error", "dsrt_stream",
     "dsrt_scene_upload", "dsrt_scene_upload_device", "dsrt_scene_stats", "dsrt_scene_download",
     "dsrt_render_frame", "dsrt_frame_stats", "dsrt_set_stage_timing", "dsrt_set_samples_per_batch",
+    "dsrt_render_frame_async", "dsrt_readback_rgb8_async", "dsrt_frame_wait", "dsrt_primary_hits",
     "dsrt_set_bvh_builder",
-    "dsrt_host_alloc", "dsrt_host_free", "dsrt_box_screen_bounds", "dsrt_readback_rgb8", "dsrt_readback_accum", "dsrt_accum_device", "dsrt_upload_accum", "dsrt_reduce_accum",
+    "dsrt_host_alloc", "dsrt_host_free", "dsrt_box_screen_bounds", "dsrt_readback_rgb8", "dsrt_readback_accum", "dsrt_accum_device", "dsrt_upload_accum", "dsrt_reduce_accum", "dsrt_clear_accum",
     "dsrt_trace_closest", "dsrt_trace_occluded", "dsrt_first_hits",
     "dsrt_trace_closest_device", "dsrt_trace_occluded_device",
     "dsrt_read_pose_file", "dsrt_pose_to_model_frame", "dsrt_camera_look_at_origin",
@@ -114,12 +115,17 @@ lib.dsrt_last_error.restype = C.c_char_p
 lib.dsrt_stream.argtypes = [_vp]
 lib.dsrt_stream.restype = _vp
 lib.dsrt_scene_upload.argtypes = [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i]
-lib.dsrt_scene_upload_device.argtypes = [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i]
+lib.dsrt_scene_upload_device.argtypes = [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i]
 lib.dsrt_scene_stats.argtypes = [_vp, C.POINTER(SceneStats)]
 lib.dsrt_scene_download.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t]
 lib.dsrt_render_frame.argtypes = [_vp, C.POINTER(Camera), C.POINTER(_f), C.POINTER(_f), _i,
                                   C.POINTER(RenderParams), C.c_uint64, _i, _i, C.POINTER(_i), _i]
 lib.dsrt_frame_stats.argtypes = [_vp, C.POINTER(FrameStats)]
+lib.dsrt_render_frame_async.argtypes = [_vp, _i, C.POINTER(Camera), C.POINTER(_f), C.POINTER(_f), _i,
+                                        C.POINTER(RenderParams), C.c_uint64, _i, _i, C.POINTER(_i), _i]
+lib.dsrt_readback_rgb8_async.argtypes = [_vp, _i, _i, _f, _vp, C.c_size_t]
+lib.dsrt_frame_wait.argtypes = [_vp, _i, C.POINTER(FrameStats)]
+lib.dsrt_primary_hits.argtypes = [_vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_uint64, _i, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.dsrt_set_stage_timing.argtypes = [_vp, _i]
 lib.dsrt_set_samples_per_batch.argtypes = [_vp, _i]
 lib.dsrt_set_bvh_builder.argtypes = [_vp, _i]
@@ -127,6 +133,8 @@ lib.dsrt_readback_rgb8.argtypes = [_vp, _i, _f, _vp, C.c_size_t]
 lib.dsrt_readback_accum.argtypes = [_vp, _vp, C.c_size_t]
 lib.dsrt_accum_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
 lib.dsrt_upload_accum.argtypes = [_vp, _vp, C.c_size_t]
+lib.dsrt_clear_accum.argtypes = [_vp, _i, _i]
+lib.dsrt_reduce_accum.argtypes = [_vp, _vp, _i]
 lib.dsrt_trace_closest.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp]
 lib.dsrt_trace_occluded.argtypes = [_vp, _vp, _i, _vp]
 lib.dsrt_first_hits.argtypes = [_vp, C.POINTER(Camera), _i, _i, _f, _f, _vp, _vp, _vp, _vp]
@@ -202,7 +210,7 @@ class MeshView(C.Structure):
     _fields_ = [("triangles", _vp), ("num_triangles", C.c_int32), ("materials", _vp), ("num_materials", C.c_int32),
                 ("textures", _vp), ("num_textures", C.c_int32), ("texture_pool", _vp), ("texture_pool_floats", C.c_int32),
                 ("num_vertices", C.c_int32), ("num_uvs", C.c_int32), ("skipped_faces", C.c_int32),
-                ("textures_failed", C.c_int32), ("textures_flipped", C.c_int32)]
+                ("textures_failed", C.c_int32), ("textures_flipped", C.c_int32), ("textures_unsupported", C.c_int32)]
 
 
 def load_obj(path, scale: float = 1.0) -> dict:
@@ -227,7 +235,8 @@ def load_obj(path, scale: float = 1.0) -> dict:
                 "textures": grab(v.textures, v.num_textures, texture_header_dtype),
                 "texture_pool": grab(v.texture_pool, v.texture_pool_floats, np.float32),
                 "num_vertices": v.num_vertices, "num_uvs": v.num_uvs, "skipped_faces": v.skipped_faces,
-                "textures_failed": v.textures_failed, "textures_flipped": bool(v.textures_flipped)}
+                "textures_failed": v.textures_failed, "textures_flipped": bool(v.textures_flipped),
+                "textures_unsupported": v.textures_unsupported}
     finally:
         lib.dsrt_mesh_free(h)
 
@@ -299,8 +308,10 @@ class Context:
                                        tp.ctypes.data if len(tp) else None, len(tp)))
         return self.scene_stats()
 
-    def upload_scene_device(self, tris_ptr: int, ntris: int, mats_ptr: int, nmats: int) -> SceneStats:
-        self._ck(lib.dsrt_scene_upload_device(self._h, tris_ptr, ntris, mats_ptr, nmats, 0, None, 0, None, 0))
+    def upload_scene_device(self, tris_ptr: int, ntris: int, mats_ptr: int, nmats: int,
+                            spheres_ptr: int = 0, nspheres: int = 0) -> SceneStats:
+        self._ck(lib.dsrt_scene_upload_device(self._h, tris_ptr, ntris, mats_ptr, nmats, spheres_ptr or None, nspheres,
+                                              None, 0, None, 0))
         return self.scene_stats()
 
     def scene_stats(self) -> SceneStats:
@@ -326,6 +337,37 @@ class Context:
                                        seed, sample_begin, sample_end, r, int(keep_accum)))
         self.width, self.height = params.img_width, params.img_height
         return self.frame_stats()
+
+    def render_async(self, slot: int, camera: Camera, sun_dir, params: RenderParams, seed=DEFAULT_SEED, sample_begin=0,
+                     sample_end=None, rect=None, keep_accum=False, sun_radiance=SUN_RADIANCE, sun_enabled=True):
+        """Enqueue a frame on `slot` (own stream and work memory) and return at once; see frame_wait."""
+        sd = (_f * 3)(*[float(x) for x in sun_dir])
+        sr = (_f * 3)(*[float(x) for x in sun_radiance])
+        if sample_end is None:
+            sample_end = max(1, params.samples_per_pixel)
+        r = (C.c_int * 4)(*rect) if rect is not None else None
+        self._ck(lib.dsrt_render_frame_async(self._h, slot, C.byref(camera), sd, sr, int(sun_enabled), C.byref(params),
+                                             seed, sample_begin, sample_end, r, int(keep_accum)))
+        self.width, self.height = params.img_width, params.img_height
+
+    def readback_rgb8_async(self, slot: int, total_spp: int, gamma: float, out: np.ndarray):
+        """Enqueue tone map + copy of the slot's frame into `out` (keep it alive until frame_wait)."""
+        self._ck(lib.dsrt_readback_rgb8_async(self._h, slot, total_spp, gamma, out.ctypes.data, out.nbytes))
+
+    def frame_wait(self, slot: int) -> FrameStats:
+        fs = FrameStats()
+        self._ck(lib.dsrt_frame_wait(self._h, slot, C.byref(fs)))
+        return fs
+
+    def primary_hits(self, camera: Camera, params: RenderParams, sample=0, seed=DEFAULT_SEED):
+        """First hits of one sample taken from the pipeline's own k_tile_entries + k_primary:
+        (tri, t, u, v, leaf_node, leaf_record), each W*H with index x + y*W (y = 0 bottom row)."""
+        n = params.img_width * params.img_height
+        tri, node, rec = (np.empty(n, np.int32) for _ in range(3))
+        t, u, v = (np.empty(n, np.float32) for _ in range(3))
+        self._ck(lib.dsrt_primary_hits(self._h, C.byref(camera), C.byref(params), seed, sample, tri.ctypes.data,
+                                       t.ctypes.data, u.ctypes.data, v.ctypes.data, node.ctypes.data, rec.ctypes.data))
+        return tri, t, u, v, node, rec
 
     def frame_stats(self) -> FrameStats:
         fs = FrameStats()

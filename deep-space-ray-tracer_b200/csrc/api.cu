@@ -32,9 +32,45 @@ constexpr int kMaxEvents = 8192;
 
 }  // namespace
 
+// Everything one frame in flight needs: its own stream, image buffers, work memory, counters and timers.
+// Slot 0 serves the synchronous calls; dsrt_render_frame_async can use any slot, and frames enqueued on
+// different slots overlap on the GPU (the latency-bound end of one frame under the camera rays of the next).
+struct FrameSlot {
+    bool created = false;
+    cudaStream_t stream = nullptr;
+    int W = 0, H = 0;
+    float* accum = nullptr;
+    uint32_t* rng_pix = nullptr;
+    unsigned char* d_rgb = nullptr;
+    uint2* tile_table = nullptr;       // per-tile traversal entry groups of the current frame (render.cu: k_tile_entries)
+    uint32_t* active_tiles = nullptr;  // tiles that need camera rays, compacted
+    size_t tile_table_tiles = 0;
+    int lcg_next_sample = -1;
+
+    size_t cap_paths = 0;
+    float4 *rq_o[2] = {nullptr, nullptr}, *rq_d[2] = {nullptr, nullptr};
+    float4 *hits = nullptr, *st_a = nullptr, *st_b = nullptr, *sq_o = nullptr, *sq_l = nullptr;
+    uint32_t* pq = nullptr;
+    uint2* dbg_leaf = nullptr;         // parity hook only
+    size_t cap_leaf = 0;
+    uint32_t* counters = nullptr;      // C_COUNT words, then the active-tile count of the frame
+    unsigned long long* stats = nullptr;
+    unsigned long long* h_stats = nullptr;     // pinned: S_COUNT statistics of the frame + 8 counter words (hooks)
+
+    cudaEvent_t ev_frame[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_kind;          // what the interval [k, k+1) measured: 0 k_trace, 1 k_shade, 2 k_primary, -1 other
+    size_t nev = 0;
+    bool pending = false;              // a frame was enqueued and not yet waited for
+    uint32_t launches = 0, batches = 0;
+    DsrtFrameStats fstats{};
+};
+
+constexpr int kMaxSlots = 4;
+
 struct dsrt_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // = slots[0].stream
     char err[512] = "";
 
     // scene
@@ -50,32 +86,16 @@ struct dsrt_ctx {
     int nspheres = 0, nsphere_lights = 0;
     DsrtSceneStats sstats{};
 
-    // frame
-    int W = 0, H = 0;
-    float* accum = nullptr;
-    uint32_t* rng_pix = nullptr;
-    unsigned char* d_rgb = nullptr;
-    uint2* tile_table = nullptr;       // per-tile traversal entry groups of the current frame (render.cu: k_tile_entries)
-    size_t tile_table_tiles = 0;
-    int use_tile_entries = 1;
-    int lcg_next_sample = -1;
-
-    size_t cap_paths = 0;
-    float4 *rq_o[2] = {nullptr, nullptr}, *rq_d[2] = {nullptr, nullptr};
-    float4 *hits = nullptr, *st_a = nullptr, *st_b = nullptr, *sq_o = nullptr, *sq_l = nullptr;
-    uint32_t* counters = nullptr;
-    unsigned long long* stats = nullptr;
-    uint32_t* h_pinned = nullptr;      // small pinned scratch for counter read-backs
+    FrameSlot slots[kMaxSlots];
 
     LaunchDims dims;
-    DsrtFrameStats fstats{};
     int stage_timing = 0;
     int spb_override = 0;
+    int use_tile_entries = 1;
     int builder = DSRT_BUILDER_PLOC;   // binary-tree stage of the BVH build (bvh_build.h)
-    int work_gb = 60;                  // work-memory budget of a batch in GB, a third of a B200's HBM (DSRT_WORK_GB)
+    int work_gb = 40;                  // work-memory budget of a batch, per slot, in GB (DSRT_WORK_GB)
     int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
-    cudaEvent_t ev_frame[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_pool;
+    int wave_depth = 16;               // bounces run as wavefront launches; deeper ones are finished by one closing k_tail
 
     // scratch for the trace hooks
     float4* t_rays = nullptr;
@@ -112,38 +132,70 @@ void free_scene(dsrt_ctx* c) {
     c->have_scene = false;
 }
 
-void free_work(dsrt_ctx* c) {
-    for (int k = 0; k < 2; ++k) { cudaFree(c->rq_o[k]); cudaFree(c->rq_d[k]); c->rq_o[k] = c->rq_d[k] = nullptr; }
-    cudaFree(c->hits); cudaFree(c->st_a); cudaFree(c->st_b); cudaFree(c->sq_o); cudaFree(c->sq_l);
-    c->hits = c->st_a = c->st_b = c->sq_o = c->sq_l = nullptr;
-    c->cap_paths = 0;
+void free_work(FrameSlot& f) {
+    for (int k = 0; k < 2; ++k) { cudaFree(f.rq_o[k]); cudaFree(f.rq_d[k]); f.rq_o[k] = f.rq_d[k] = nullptr; }
+    cudaFree(f.hits); cudaFree(f.st_a); cudaFree(f.st_b); cudaFree(f.sq_o); cudaFree(f.sq_l); cudaFree(f.pq);
+    f.hits = f.st_a = f.st_b = f.sq_o = f.sq_l = nullptr;
+    f.pq = nullptr;
+    f.cap_paths = 0;
 }
 
-int ensure_work(dsrt_ctx* ctx, size_t paths) {
-    if (paths <= ctx->cap_paths) return DSRT_OK;
-    free_work(ctx);
-    const size_t b = paths * sizeof(float4);
-    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&ctx->rq_o[k], b)); CK(cudaMalloc(&ctx->rq_d[k], b)); }
-    CK(cudaMalloc(&ctx->hits, b));
-    CK(cudaMalloc(&ctx->st_a, b));
-    CK(cudaMalloc(&ctx->st_b, b));
-    CK(cudaMalloc(&ctx->sq_o, b));
-    CK(cudaMalloc(&ctx->sq_l, b));
-    ctx->cap_paths = paths;
+void free_slot(FrameSlot& f) {
+    if (!f.created) return;
+    if (f.stream) cudaStreamSynchronize(f.stream);
+    free_work(f);
+    cudaFree(f.accum); cudaFree(f.rng_pix); cudaFree(f.d_rgb); cudaFree(f.tile_table); cudaFree(f.active_tiles);
+    cudaFree(f.dbg_leaf);
+    cudaFree(f.counters); cudaFree(f.stats);
+    if (f.h_stats) cudaFreeHost(f.h_stats);
+    for (cudaEvent_t e : f.ev_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) if (f.ev_frame[k]) cudaEventDestroy(f.ev_frame[k]);
+    if (f.stream) cudaStreamDestroy(f.stream);
+    f = FrameSlot();
+}
+
+int slot_init(dsrt_ctx* ctx, int k) {
+    FrameSlot& f = ctx->slots[k];
+    if (f.created) return DSRT_OK;
+    f.created = true;
+    CK(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&f.counters, sizeof(uint32_t) * (C_COUNT + 8)));
+    CK(cudaMemset(f.counters, 0, sizeof(uint32_t) * (C_COUNT + 8)));
+    CK(cudaMalloc(&f.stats, sizeof(unsigned long long) * S_COUNT));
+    CK(cudaMallocHost(&f.h_stats, sizeof(unsigned long long) * (S_COUNT + 8)));
+    CK(cudaEventCreate(&f.ev_frame[0]));
+    CK(cudaEventCreate(&f.ev_frame[1]));
     return DSRT_OK;
 }
 
-int ensure_image(dsrt_ctx* ctx, int W, int H, bool* fresh) {
+constexpr long long kWorkBytesPerPath = 9 * 16 + 4;      // what ensure_work allocates per path
+
+int ensure_work(dsrt_ctx* ctx, FrameSlot& f, size_t paths) {
+    if (paths <= f.cap_paths) return DSRT_OK;
+    free_work(f);
+    const size_t b = paths * sizeof(float4);
+    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&f.rq_o[k], b)); CK(cudaMalloc(&f.rq_d[k], b)); }
+    CK(cudaMalloc(&f.hits, b));
+    CK(cudaMalloc(&f.st_a, b));
+    CK(cudaMalloc(&f.st_b, b));
+    CK(cudaMalloc(&f.sq_o, b));
+    CK(cudaMalloc(&f.sq_l, b));
+    CK(cudaMalloc(&f.pq, paths * sizeof(uint32_t)));
+    f.cap_paths = paths;
+    return DSRT_OK;
+}
+
+int ensure_image(dsrt_ctx* ctx, FrameSlot& f, int W, int H, bool* fresh) {
     *fresh = false;
-    if (ctx->accum && ctx->W == W && ctx->H == H) return DSRT_OK;
-    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb);
-    ctx->accum = nullptr; ctx->rng_pix = nullptr; ctx->d_rgb = nullptr;
+    if (f.accum && f.W == W && f.H == H) return DSRT_OK;
+    cudaFree(f.accum); cudaFree(f.rng_pix); cudaFree(f.d_rgb);
+    f.accum = nullptr; f.rng_pix = nullptr; f.d_rgb = nullptr;
     const size_t px = (size_t)W * H;
-    CK(cudaMalloc(&ctx->accum, px * 3 * sizeof(float)));
-    CK(cudaMalloc(&ctx->rng_pix, px * sizeof(uint32_t)));
-    CK(cudaMalloc(&ctx->d_rgb, px * 3));
-    ctx->W = W; ctx->H = H;
-    ctx->lcg_next_sample = -1;
+    CK(cudaMalloc(&f.accum, px * 3 * sizeof(float)));
+    CK(cudaMalloc(&f.rng_pix, px * sizeof(uint32_t)));
+    CK(cudaMalloc(&f.d_rgb, px * 3));
+    f.W = W; f.H = H;
+    f.lcg_next_sample = -1;
     *fresh = true;
     return DSRT_OK;
 }
@@ -169,13 +221,19 @@ void host_ldir(const float s[3], float out[3]) {
     out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
 }
 
-cudaEvent_t pool_event(dsrt_ctx* c, size_t i) {
-    while (c->ev_pool.size() <= i) {
+cudaEvent_t pool_event(FrameSlot& f, size_t i) {
+    while (f.ev_pool.size() <= i) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-        c->ev_pool.push_back(e);
+        f.ev_pool.push_back(e);
     }
-    return c->ev_pool[i];
+    return f.ev_pool[i];
+}
+
+int sync_all_slots(dsrt_ctx* ctx) {
+    for (int k = 0; k < kMaxSlots; ++k)
+        if (ctx->slots[k].created) CK(cudaStreamSynchronize(ctx->slots[k].stream));
+    return DSRT_OK;
 }
 
 }  // namespace
@@ -199,22 +257,18 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     ctx = new (std::nothrow) dsrt_ctx();
     if (!ctx) return fail(nullptr, DSRT_ENOMEM, "out of host memory");
     ctx->device = device;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMalloc(&ctx->counters, sizeof(uint32_t) * C_COUNT) == cudaSuccess &&
-              cudaMemset(ctx->counters, 0, sizeof(uint32_t) * C_COUNT) == cudaSuccess &&
-              cudaMalloc(&ctx->stats, sizeof(unsigned long long) * S_COUNT) == cudaSuccess &&
-              cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint32_t)) == cudaSuccess &&
-              cudaEventCreate(&ctx->ev_frame[0]) == cudaSuccess &&
-              cudaEventCreate(&ctx->ev_frame[1]) == cudaSuccess;
-    if (!ok) {
-        fail(nullptr, DSRT_ECUDA, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (slot_init(ctx, 0) != DSRT_OK) {
+        fail(nullptr, DSRT_ECUDA, "context set-up failed: %s", ctx->err);
         dsrt_destroy(ctx);
         return DSRT_ECUDA;
     }
+    ctx->stream = ctx->slots[0].stream;
     launch_dims(&ctx->dims, device);
-    if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);      // tuning experiments only
-    if (const char* e = getenv("DSRT_TILE_ENTRIES")) ctx->use_tile_entries = atoi(e) != 0;     // A/B runs
+    // tuning / A-B switches for experiments; none is needed for normal use
+    if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);
+    if (const char* e = getenv("DSRT_TILE_ENTRIES")) ctx->use_tile_entries = atoi(e) != 0;
     if (const char* e = getenv("DSRT_WORK_GB")) ctx->work_gb = std::max(1, std::min(120, atoi(e)));
+    if (const char* e = getenv("DSRT_WAVE_DEPTH")) ctx->wave_depth = std::max(2, atoi(e));
     if (const char* e = getenv("DSRT_BVH_BUILDER")) ctx->builder = strcmp(e, "lbvh") == 0 ? DSRT_BUILDER_LBVH : DSRT_BUILDER_PLOC;
     *out = ctx;
     return DSRT_OK;
@@ -223,22 +277,22 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
 extern "C" void dsrt_destroy(dsrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < kMaxSlots; ++k)
+        if (ctx->slots[k].created && ctx->slots[k].stream) cudaStreamSynchronize(ctx->slots[k].stream);
     free_scene(ctx);
-    free_work(ctx);
-    cudaFree(ctx->accum); cudaFree(ctx->rng_pix); cudaFree(ctx->d_rgb); cudaFree(ctx->tile_table);
-    cudaFree(ctx->counters); cudaFree(ctx->stats);
+    for (int k = 0; k < kMaxSlots; ++k) free_slot(ctx->slots[k]);
     cudaFree(ctx->t_rays); cudaFree(ctx->t_hits); cudaFree(ctx->t_occ);
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    for (int k = 0; k < 2; ++k) if (ctx->ev_frame[k]) cudaEventDestroy(ctx->ev_frame[k]);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" void* dsrt_stream(dsrt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 namespace {
+
+__global__ void k_check_material_ids(const DsrtTriangle* __restrict__ tris, int n, int nmats, uint32_t* bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (tris[i].material_id < 0 || tris[i].material_id >= nmats)) atomicAdd(bad, 1u);
+}
 
 // Common tail of the two upload entry points.  `tris`/`mats`/`textures`/`pool` are host
 // pointers when from_device is false and device pointers (on ctx's GPU) when it is true.
@@ -250,8 +304,19 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
         return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad triangle/material arguments");
     if ((ntris > 0 || nspheres > 0) && nmats == 0) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: geometry without materials");
     if (nspheres < 0 || (nspheres > 0 && !spheres)) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad sphere arguments");
-    if (nspheres > 0 && from_device)
-        return fail(ctx, DSRT_EUNSUPPORTED, "dsrt_scene_upload_device takes no spheres (they are packed on the host)");
+    // Spheres are few and are packed on the host (with the material table at hand, for the emissive ones): arrays that
+    // live on the device come back first.
+    std::vector<DsrtSphere> h_spheres;
+    std::vector<DsrtMaterial> h_mats;
+    if (from_device && nspheres > 0) {
+        CK(cudaSetDevice(ctx->device));
+        h_spheres.resize((size_t)nspheres);
+        h_mats.resize((size_t)nmats);
+        CK(cudaMemcpy(h_spheres.data(), spheres, sizeof(DsrtSphere) * (size_t)nspheres, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h_mats.data(), mats, sizeof(DsrtMaterial) * (size_t)nmats, cudaMemcpyDeviceToHost));
+        spheres = h_spheres.data();
+    }
+    const DsrtMaterial* mats_host = (from_device && nspheres > 0) ? h_mats.data() : mats;
     for (int i = 0; i < nspheres; ++i)
         if (spheres[i].material_id < 0 || spheres[i].material_id >= nmats)
             return fail(ctx, DSRT_EINVAL, "sphere %d has material_id %d outside [0,%d)", i, spheres[i].material_id, nmats);
@@ -262,7 +327,12 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
             if (tris[i].material_id < 0 || tris[i].material_id >= nmats)
                 return fail(ctx, DSRT_EINVAL, "triangle %d has material_id %d outside [0,%d)", i, tris[i].material_id, nmats);
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rc = sync_all_slots(ctx);      // no frame may be in flight on the scene that is replaced
+        if (rc) return rc;
+    }
     free_scene(ctx);
+    cudaEvent_t* ev_frame = ctx->slots[0].ev_frame;
     const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 
     DsrtSceneStats st{};
@@ -295,7 +365,7 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
             float mid;
             memcpy(&mid, &sp.material_id, 4);
             rec[2 * i + 1] = make_float4(1.0f / sp.radius, mid, 0.f, 0.f);       // IEEE division, as :501
-            const DsrtMaterial& m = mats[sp.material_id];
+            const DsrtMaterial& m = mats_host[sp.material_id];
             if (m.type == DSRT_MAT_DIFFUSE_LIGHT && (m.emissive.x > 0 || m.emissive.y > 0 || m.emissive.z > 0))
                 lights.push_back(i);
         }
@@ -313,12 +383,23 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
         DsrtTriangle* d_raw = nullptr;
         if (!from_device) {
             CK(cudaMalloc(&d_raw, sizeof(DsrtTriangle) * (size_t)ntris));
-            cudaEventRecord(ctx->ev_frame[0], ctx->stream);
+            cudaEventRecord(ev_frame[0], ctx->stream);
             cudaError_t e = cudaMemcpyAsync(d_raw, tris, sizeof(DsrtTriangle) * (size_t)ntris, cudaMemcpyHostToDevice, ctx->stream);
-            cudaEventRecord(ctx->ev_frame[1], ctx->stream);
+            cudaEventRecord(ev_frame[1], ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { cudaFree(d_raw); return fail(ctx, DSRT_ECUDA, "triangle upload: %s", cudaGetErrorString(e)); }
-            cudaEventElapsedTime(&st.upload_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
+            cudaEventElapsedTime(&st.upload_ms, ev_frame[0], ev_frame[1]);
+        }
+        if (from_device) {
+            // the host path range-checks material ids above; here a kernel does (an id outside the table would index
+            // past the material array in k_shade)
+            uint32_t* flag = ctx->slots[0].counters + C_COUNT + 1;
+            CK(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream));
+            k_check_material_ids<<<(ntris + 255) / 256, 256, 0, ctx->stream>>>(tris, ntris, nmats, flag);
+            uint32_t bad = 0;
+            CK(cudaMemcpyAsync(&bad, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (bad != 0u) return fail(ctx, DSRT_EINVAL, "%u triangles have a material_id outside [0,%d)", bad, nmats);
         }
         char msg[256] = "";
         int rc = build_bvh8(ctx->stream, from_device ? tris : d_raw, ntris, ntextures > 0, ctx->builder, &ctx->bvh, msg, sizeof(msg));
@@ -351,11 +432,12 @@ extern "C" int dsrt_scene_upload(dsrt_ctx* ctx, const DsrtTriangle* tris, int nt
 }
 
 extern "C" int dsrt_scene_upload_device(dsrt_ctx* ctx, const DsrtTriangle* tris_device, int ntris,
-                                        const DsrtMaterial* mats_device, int nmats, int nspheres,
+                                        const DsrtMaterial* mats_device, int nmats,
+                                        const DsrtSphere* spheres_device, int nspheres,
                                         const DsrtTextureHeader* textures_device, int ntextures,
                                         const float* texture_pool_device, int texture_pool_floats) {
     if (!ctx) return DSRT_EINVAL;
-    return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, nullptr, nspheres,
+    return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, spheres_device, nspheres,
                              textures_device, ntextures, texture_pool_device, texture_pool_floats);
 }
 
@@ -469,84 +551,141 @@ void fill_camera(const DsrtCamera* cam, FrameConst& fc) {
 
 }  // namespace
 
-extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
-                                 const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
-                                 const DsrtRenderParams* params, uint64_t seed,
-                                 int sample_begin, int sample_end, const int rect[4], int keep_accum) {
-    if (!ctx) return DSRT_EINVAL;
+namespace {
+
+// What one frame call asks for, validated.
+struct FrameArgs {
+    int W, H, spp_total, x0, y0, x1, y1, rng_mode, sample_begin, sample_end, sun_enabled;
+    bool full_rect;
+};
+
+int check_frame_args(dsrt_ctx* ctx, const DsrtCamera* camera, const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                     const DsrtRenderParams* params, int sample_begin, int sample_end, const int rect[4], FrameArgs* a) {
     if (!camera || !params) return fail(ctx, DSRT_EINVAL, "dsrt_render_frame: camera/params NULL");
     if (!ctx->have_scene) return fail(ctx, DSRT_ENOSCENE, "dsrt_render_frame before dsrt_scene_upload");
-    const int W = params->img_width > 0 ? params->img_width : camera->image_width;
-    const int H = params->img_height > 0 ? params->img_height : camera->image_height;
-    if (W < 2 || H < 2) return fail(ctx, DSRT_EINVAL, "image must be at least 2x2 (got %dx%d)", W, H);
-    const int spp_total = params->samples_per_pixel < 1 ? 1 : params->samples_per_pixel;
-    if (sample_begin < 0 || sample_end < sample_begin || sample_end > spp_total)
-        return fail(ctx, DSRT_EINVAL, "sample range [%d,%d) outside [0,%d)", sample_begin, sample_end, spp_total);
-    int x0 = 0, y0 = 0, x1 = W, y1 = H;
-    if (rect) { x0 = rect[0]; y0 = rect[1]; x1 = rect[2]; y1 = rect[3]; }
-    if (x0 < 0 || y0 < 0 || x1 > W || y1 > H || x1 <= x0 || y1 <= y0)
-        return fail(ctx, DSRT_EINVAL, "bad rectangle [%d,%d)x[%d,%d) for %dx%d", x0, x1, y0, y1, W, H);
+    a->W = params->img_width > 0 ? params->img_width : camera->image_width;
+    a->H = params->img_height > 0 ? params->img_height : camera->image_height;
+    if (a->W < 2 || a->H < 2) return fail(ctx, DSRT_EINVAL, "image must be at least 2x2 (got %dx%d)", a->W, a->H);
+    a->spp_total = params->samples_per_pixel < 1 ? 1 : params->samples_per_pixel;
+    if (sample_begin < 0 || sample_end < sample_begin || sample_end > a->spp_total)
+        return fail(ctx, DSRT_EINVAL, "sample range [%d,%d) outside [0,%d)", sample_begin, sample_end, a->spp_total);
+    a->sample_begin = sample_begin; a->sample_end = sample_end;
+    a->x0 = 0; a->y0 = 0; a->x1 = a->W; a->y1 = a->H;
+    if (rect) { a->x0 = rect[0]; a->y0 = rect[1]; a->x1 = rect[2]; a->y1 = rect[3]; }
+    if (a->x0 < 0 || a->y0 < 0 || a->x1 > a->W || a->y1 > a->H || a->x1 <= a->x0 || a->y1 <= a->y0)
+        return fail(ctx, DSRT_EINVAL, "bad rectangle [%d,%d)x[%d,%d) for %dx%d", a->x0, a->x1, a->y0, a->y1, a->W, a->H);
     if (sun_enabled && (!sun_dir || !sun_radiance)) return fail(ctx, DSRT_EINVAL, "sun enabled but sun_dir/sun_radiance NULL");
-    const int rng_mode = params->rng_mode;
-    if (rng_mode != DSRT_RNG_PHILOX && rng_mode != DSRT_RNG_REF_LCG)
-        return fail(ctx, DSRT_EINVAL, "unknown rng_mode %d", rng_mode);
+    a->sun_enabled = sun_enabled ? 1 : 0;
+    a->rng_mode = params->rng_mode;
+    if (a->rng_mode != DSRT_RNG_PHILOX && a->rng_mode != DSRT_RNG_REF_LCG)
+        return fail(ctx, DSRT_EINVAL, "unknown rng_mode %d", a->rng_mode);
+    a->full_rect = (a->x0 == 0 && a->y0 == 0 && a->x1 == a->W && a->y1 == a->H);
+    return DSRT_OK;
+}
 
-    CK(cudaSetDevice(ctx->device));
-    bool fresh = false;
-    int rc = ensure_image(ctx, W, H, &fresh);
-    if (rc) return rc;
-    if (fresh || !keep_accum)
-        CK(cudaMemsetAsync(ctx->accum, 0, (size_t)W * H * 3 * sizeof(float), ctx->stream));
-
-    const bool full_rect = (x0 == 0 && y0 == 0 && x1 == W && y1 == H);
-    if (rng_mode == DSRT_RNG_REF_LCG) {
-        // The replay keeps one generator per pixel that runs through the samples in order.
-        if (sample_begin == 0) {
-            launch_lcg_seed(ctx->rng_pix, W, H, (uint32_t)(seed & 0xFFFFFFFFu), ctx->stream);
-        } else if (sample_begin != ctx->lcg_next_sample || !full_rect) {
-            return fail(ctx, DSRT_EINVAL, "LCG replay renders samples in order from 0 (next expected %d, got %d)",
-                        ctx->lcg_next_sample, sample_begin);
-        }
-        ctx->lcg_next_sample = full_rect ? sample_end : -1;
-    }
-
-    FrameConst fc;
+// The frame constants that do not depend on the slot's work memory.
+void fill_frame_consts(dsrt_ctx* ctx, const FrameArgs& a, const DsrtCamera* camera, const float sun_dir[3], const float sun_radiance[3],
+                       const DsrtRenderParams* params, uint64_t seed, FrameConst& fc) {
     memset(&fc, 0, sizeof(fc));
     fill_scene_consts(ctx, fc);
     fill_camera(camera, fc);
-    fc.W = W; fc.H = H;
-    fc.x0 = x0; fc.y0 = y0; fc.rw = x1 - x0; fc.rh = y1 - y0;
+    fc.W = a.W; fc.H = a.H;
+    fc.x0 = a.x0; fc.y0 = a.y0; fc.rw = a.x1 - a.x0; fc.rh = a.y1 - a.y0;
     {
         int hb[4];
-        const bool bounded = scene_screen_bounds(fc, W, H, hb);
+        const bool bounded = scene_screen_bounds(fc, a.W, a.H, hb);
         fc.hit_x0 = hb[0]; fc.hit_y0 = hb[1]; fc.hit_x1 = hb[2]; fc.hit_y1 = hb[3];
-        fc.cull_pixels = (bounded && fc.num_spheres == 0 && rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
+        fc.cull_pixels = (bounded && fc.num_spheres == 0 && a.rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
     }
     fc.tiles_x = (fc.rw + 7) / 8;
     const int tiles_y = (fc.rh + 3) / 4;
     fc.slots_per_sample = fc.tiles_x * tiles_y * 32;
     fc.inv_tiles_x = 1.0f / (float)fc.tiles_x;
     fc.inv_slots_per_sample = 1.0f / (float)fc.slots_per_sample;
-    fc.spp_total = spp_total;
+    fc.spp_total = a.spp_total;
     fc.max_depth = params->max_depth > 0 ? params->max_depth : 12;
-    fc.rng_mode = rng_mode;
+    fc.rng_mode = a.rng_mode;
     fc.seed_lo = (uint32_t)(seed & 0xFFFFFFFFu);
     fc.seed_hi = (uint32_t)(seed >> 32);
-    fc.sun_enabled = sun_enabled ? 1 : 0;
-    if (sun_enabled) {
+    fc.sun_enabled = a.sun_enabled;
+    if (a.sun_enabled) {
         host_ldir(sun_dir, fc.ldir);
-        for (int a = 0; a < 3; ++a) fc.sun_rad[a] = sun_radiance[a];
+        for (int k = 0; k < 3; ++k) fc.sun_rad[k] = sun_radiance[k];
     }
+    // camera rays start at per-tile entry nodes, and tiles with nothing in sight are skipped outright -- unless the
+    // scene has spheres (they lie outside the triangle BVH) or the LCG replay runs (its generator advances per pixel)
+    fc.tile_walk = (ctx->use_tile_entries && fc.num_nodes > 0) ? 1 : 0;
+    fc.cull_tiles = (fc.tile_walk && fc.num_spheres == 0 && a.rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
+}
+
+void bind_slot(FrameSlot& f, FrameConst& fc) {
+    for (int k = 0; k < 2; ++k) { fc.rq_o[k] = f.rq_o[k]; fc.rq_d[k] = f.rq_d[k]; }
+    fc.hits = f.hits; fc.st_a = f.st_a; fc.st_b = f.st_b; fc.sq_o = f.sq_o; fc.sq_l = f.sq_l;
+    fc.pq = f.pq;
+    fc.dbg_leaf = nullptr;
+    fc.rng_pix = f.rng_pix;
+    fc.accum = f.accum;
+    fc.counters = f.counters;
+    fc.n_active = f.counters + C_COUNT;
+    fc.stats = f.stats;
+    fc.tile_entries = f.tile_table;
+    fc.active_tiles = f.active_tiles;
+}
+
+int ensure_tiles(dsrt_ctx* ctx, FrameSlot& f, const FrameConst& fc) {
+    const size_t ntiles = (size_t)fc.slots_per_sample >> 5;
+    if (ntiles <= f.tile_table_tiles) return DSRT_OK;
+    cudaFree(f.tile_table); cudaFree(f.active_tiles);
+    f.tile_table = nullptr; f.active_tiles = nullptr; f.tile_table_tiles = 0;
+    CK(cudaMalloc(&f.tile_table, ntiles * 8 * sizeof(uint2)));       // up to 8 start nodes per tile (render.cu: DSRT_TILE_ENTRY_COUNT)
+    CK(cudaMalloc(&f.active_tiles, ntiles * sizeof(uint32_t)));
+    f.tile_table_tiles = ntiles;
+    return DSRT_OK;
+}
+
+// Enqueues one frame on the slot's stream.  No host synchronisation: queue sizes live in device memory, the launch
+// sequence is fixed, and launches behind an emptied queue are no-ops.
+int enqueue_frame(dsrt_ctx* ctx, int slot, const DsrtCamera* camera,
+                  const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                  const DsrtRenderParams* params, uint64_t seed,
+                  int sample_begin, int sample_end, const int rect[4], int keep_accum) {
+    FrameArgs a;
+    int rc = check_frame_args(ctx, camera, sun_dir, sun_radiance, sun_enabled, params, sample_begin, sample_end, rect, &a);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    rc = slot_init(ctx, slot);
+    if (rc) return rc;
+    FrameSlot& f = ctx->slots[slot];
+    if (f.pending) return fail(ctx, DSRT_EINVAL, "slot %d still has a frame in flight: call dsrt_frame_wait first", slot);
+    bool fresh = false;
+    rc = ensure_image(ctx, f, a.W, a.H, &fresh);
+    if (rc) return rc;
+    if (fresh || !keep_accum)
+        CK(cudaMemsetAsync(f.accum, 0, (size_t)a.W * a.H * 3 * sizeof(float), f.stream));
+
+    if (a.rng_mode == DSRT_RNG_REF_LCG) {
+        // The replay keeps one generator per pixel that runs through the samples in order.
+        if (a.sample_begin == 0) {
+            launch_lcg_seed(f.rng_pix, a.W, a.H, (uint32_t)(seed & 0xFFFFFFFFu), f.stream);
+        } else if (a.sample_begin != f.lcg_next_sample || !a.full_rect) {
+            return fail(ctx, DSRT_EINVAL, "LCG replay renders samples in order from 0 (next expected %d, got %d)",
+                        f.lcg_next_sample, a.sample_begin);
+        }
+        f.lcg_next_sample = a.full_rect ? a.sample_end : -1;
+    }
+
+    FrameConst fc;
+    fill_frame_consts(ctx, a, camera, sun_dir, sun_radiance, params, seed, fc);
 
     // Samples of a pixel in flight together.  Large batches keep the deep-bounce launches
     // (few surviving rays) big enough to fill the GPU (profiles/r01_a: 2x from spb 4 -> 32);
-    // the default takes as many samples as fit the work-memory budget (144 B per path; ctx->work_gb).
+    // the default takes as many samples as fit the work-memory budget (ctx->work_gb per slot).
     int spb = 1;
-    const int nsamples = sample_end - sample_begin;
-    if (rng_mode == DSRT_RNG_PHILOX) {
+    const int nsamples = a.sample_end - a.sample_begin;
+    if (a.rng_mode == DSRT_RNG_PHILOX) {
         if (ctx->spb_override > 0) spb = ctx->spb_override;
         else {
-            const long long target = (long long)ctx->work_gb * 1000 * 1000 * 1000 / 144;
+            const long long target = (long long)ctx->work_gb * 1000 * 1000 * 1000 / kWorkBytesPerPath;
             spb = (int)std::max(1ll, std::min(256ll, target / std::max(1, fc.slots_per_sample)));
         }
         spb = std::max(1, std::min(spb, std::max(1, nsamples)));
@@ -557,123 +696,180 @@ extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
         }
     }
     // The budget is a wish, not a requirement: when the device cannot give that much (another
-    // process on the GPU), halve the batch until the allocation succeeds.
+    // process on the GPU, another slot), halve the batch until the allocation succeeds.
     for (;;) {
-        rc = ensure_work(ctx, (size_t)fc.slots_per_sample * spb);
-        if (rc == DSRT_OK || spb == 1 || rng_mode != DSRT_RNG_PHILOX) break;
+        rc = ensure_work(ctx, f, (size_t)fc.slots_per_sample * spb);
+        if (rc == DSRT_OK || spb == 1 || a.rng_mode != DSRT_RNG_PHILOX) break;
         cudaGetLastError();           // clear the allocation failure
         spb = (spb + 1) / 2;
     }
     if (rc) return rc;
-    for (int k = 0; k < 2; ++k) { fc.rq_o[k] = ctx->rq_o[k]; fc.rq_d[k] = ctx->rq_d[k]; }
-    fc.hits = ctx->hits; fc.st_a = ctx->st_a; fc.st_b = ctx->st_b; fc.sq_o = ctx->sq_o; fc.sq_l = ctx->sq_l;
-    fc.rng_pix = ctx->rng_pix;
-    fc.accum = ctx->accum;
-    fc.counters = ctx->counters;
-    fc.stats = ctx->stats;
+    rc = ensure_tiles(ctx, f, fc);
+    if (rc) return rc;
+    bind_slot(f, fc);
 
-    CK(cudaMemsetAsync(ctx->stats, 0, sizeof(unsigned long long) * S_COUNT, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_frame[0], ctx->stream));
+    CK(cudaMemsetAsync(f.stats, 0, sizeof(unsigned long long) * S_COUNT, f.stream));
+    CK(cudaEventRecord(f.ev_frame[0], f.stream));
 
-    // traversal entry points of the camera rays, per 8x4-pixel tile of the rectangle (part of the frame's device time)
-    uint32_t tile_launches = 0;
-    fc.tile_entries = nullptr;
-    fc.cull_tiles = 0;
-    if (ctx->use_tile_entries && fc.num_nodes > 0) {
-        const size_t ntiles = (size_t)fc.slots_per_sample >> 5;
-        if (ntiles > ctx->tile_table_tiles) {
-            cudaFree(ctx->tile_table);
-            ctx->tile_table = nullptr; ctx->tile_table_tiles = 0;
-            CK(cudaMalloc(&ctx->tile_table, ntiles * 8 * sizeof(uint2)));       // up to 8 start nodes per tile (render.cu: DSRT_TILE_ENTRY_COUNT)
-            ctx->tile_table_tiles = ntiles;
-        }
-        launch_tile_entries(fc, ctx->tile_table, ctx->stream);
-        tile_launches = 1;
-        fc.tile_entries = ctx->tile_table;
-        fc.cull_tiles = (fc.num_spheres == 0 && rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
-    }
+    // traversal entry points of the camera rays and the list of tiles with anything in sight, per 8x4-pixel tile of
+    // the rectangle (part of the frame's device time)
+    launch_tile_entries(fc, f.tile_table, f.active_tiles, f.stream);
 
-    uint32_t launches = tile_launches, batches = 0;
-    size_t nev = 0;                 // events used from the pool
-    std::vector<int> ev_kind;       // what the interval [k, k+1) measured: 0 k_trace, 1 k_shade, 2 k_primary, -1 other
+    uint32_t launches = 1, batches = 0;
+    f.nev = 0;
+    f.ev_kind.clear();
     const bool timing = ctx->stage_timing != 0;
     auto mark = [&](int kind_of_next_interval) {
-        if (!timing || nev >= (size_t)kMaxEvents) return;
-        cudaEvent_t e = pool_event(ctx, nev);
+        if (!timing || f.nev >= (size_t)kMaxEvents) return;
+        cudaEvent_t e = pool_event(f, f.nev);
         if (!e) return;
-        cudaEventRecord(e, ctx->stream);
-        ev_kind.push_back(kind_of_next_interval);
-        ++nev;
+        cudaEventRecord(e, f.stream);
+        f.ev_kind.push_back(kind_of_next_interval);
+        ++f.nev;
     };
 
-    for (int s0 = sample_begin; s0 < sample_end; s0 += spb) {
+    const int wave_depth = std::min(fc.max_depth, ctx->wave_depth);
+    for (int s0 = a.sample_begin; s0 < a.sample_end; s0 += spb) {
         fc.s0 = s0;
-        fc.spb = std::min(spb, sample_end - s0);
-        launch_batch_begin(fc, ctx->stream);
+        fc.spb = std::min(spb, a.sample_end - s0);
+        launch_batch_begin(fc, f.stream);
         mark(2);
-        launch_primary(fc, ctx->dims, ctx->stream);
+        launch_primary(fc, ctx->dims, false, f.stream);
         launches += 2;
         int cur = 0;
-        for (int depth = 0; depth < fc.max_depth; ++depth) {
+        for (int depth = 0; depth < wave_depth; ++depth) {
             mark(1);
-            launch_shade(fc, cur, depth, ctx->dims, ctx->stream);
+            launch_shade(fc, cur, depth, ctx->dims, f.stream);
             mark(-1);
-            launch_advance(fc, depth, ctx->stream);
+            launch_advance(fc, depth, f.stream);
             mark(0);
-            launch_trace(fc, cur ^ 1, depth & 1, ctx->dims, ctx->stream);
+            launch_trace(fc, cur ^ 1, depth & 1, ctx->dims, f.stream);
             launches += 3;
             cur ^= 1;
-            // Few rays left: one thread per path finishes them in a single launch (render.cu: k_tail).
-            if (depth >= 1 && depth + 1 < fc.max_depth && ctx->tail_threshold > 0) {
-                launch_tail(fc, cur, depth + 1, (uint32_t)ctx->tail_threshold, ctx->stream);
+            if (depth + 1 >= fc.max_depth) break;
+            // Few rays left: one thread per path finishes them in a single launch (render.cu: k_tail).  Past the
+            // wavefront depth the closing launch takes whatever is left, so no launch count depends on the queue
+            // sizes and the host never waits inside a frame.
+            const bool closing = depth + 1 == wave_depth;
+            if (closing) {
+                mark(0);
+                launch_tail(fc, cur, depth + 1, kTailAll, ctx->dims, f.stream);
                 ++launches;
-            }
-            // Stop enqueueing once nothing is in flight (checked every fourth bounce: one host sync).
-            if ((depth & 3) == 3 && depth + 1 < fc.max_depth) {
-                CK(cudaMemcpyAsync(ctx->h_pinned, ctx->counters, sizeof(uint32_t) * C_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                if (ctx->h_pinned[C_NIN] == 0u) break;      // shadow rays of this bounce were traced above
+            } else if (depth >= 1 && ctx->tail_threshold > 0) {
+                launch_tail(fc, cur, depth + 1, (uint32_t)ctx->tail_threshold, ctx->dims, f.stream);
+                ++launches;
             }
         }
         mark(-1);
-        launch_resolve(fc, ctx->dims, ctx->stream);
+        launch_resolve(fc, ctx->dims, f.stream);
         ++launches;
         ++batches;
     }
     mark(-1);
-    CK(cudaEventRecord(ctx->ev_frame[1], ctx->stream));
+    CK(cudaEventRecord(f.ev_frame[1], f.stream));
     CK(cudaGetLastError());
-    unsigned long long hs[S_COUNT];
-    CK(cudaMemcpyAsync(hs, ctx->stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(f.h_stats, f.stats, sizeof(unsigned long long) * S_COUNT, cudaMemcpyDeviceToHost, f.stream));
+    f.launches = launches;
+    f.batches = batches;
+    f.pending = true;
+    return DSRT_OK;
+}
 
+// Waits for everything enqueued on the slot and collects the frame's statistics.
+int finish_frame(dsrt_ctx* ctx, int slot) {
+    FrameSlot& f = ctx->slots[slot];
+    if (!f.created) return fail(ctx, DSRT_EINVAL, "slot %d was never used", slot);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(f.stream));
+    if (!f.pending) return DSRT_OK;
+    f.pending = false;
     DsrtFrameStats fs{};
-    fs.primary_rays = hs[S_PRIMARY];
-    fs.bounce_rays = hs[S_BOUNCE];
-    fs.shadow_rays = hs[S_SHADOW];
-    fs.paths = hs[S_PATHS];
-    fs.culled_primary_rays = hs[S_CULLED];
-    fs.kernel_launches = launches;
-    fs.batches = batches;
-    cudaEventElapsedTime(&fs.device_ms, ctx->ev_frame[0], ctx->ev_frame[1]);
-    if (timing) {
+    fs.primary_rays = f.h_stats[S_PRIMARY];
+    fs.bounce_rays = f.h_stats[S_BOUNCE];
+    fs.shadow_rays = f.h_stats[S_SHADOW];
+    fs.paths = f.h_stats[S_PATHS];
+    fs.culled_primary_rays = f.h_stats[S_CULLED];
+    fs.kernel_launches = f.launches;
+    fs.batches = f.batches;
+    cudaEventElapsedTime(&fs.device_ms, f.ev_frame[0], f.ev_frame[1]);
+    if (f.nev > 1) {
         float trav = 0.f, shade = 0.f, prim = 0.f;
-        for (size_t k = 0; k + 1 < nev; ++k) {
+        for (size_t k = 0; k + 1 < f.nev; ++k) {
             float ms = 0.f;
-            if (ev_kind[k] < 0) continue;
-            cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-            if (ev_kind[k] == 1) shade += ms; else trav += ms;
-            if (ev_kind[k] == 2) prim += ms;
+            if (f.ev_kind[k] < 0) continue;
+            cudaEventElapsedTime(&ms, f.ev_pool[k], f.ev_pool[k + 1]);
+            if (f.ev_kind[k] == 1) shade += ms; else trav += ms;
+            if (f.ev_kind[k] == 2) prim += ms;
         }
         fs.extend_ms = trav; fs.primary_ms = prim; fs.shade_ms = shade;
     }
-    ctx->fstats = fs;
+    f.fstats = fs;
+    return DSRT_OK;
+}
+
+int check_slot(dsrt_ctx* ctx, int slot) {
+    if (slot < 0 || slot >= kMaxSlots) return fail(ctx, DSRT_EINVAL, "slot %d outside [0,%d)", slot, kMaxSlots);
+    return DSRT_OK;
+}
+
+int readback_rgb8_impl(dsrt_ctx* ctx, int slot, int total_spp, float gamma, unsigned char* dst, size_t bytes, bool wait) {
+    FrameSlot& f = ctx->slots[slot];
+    if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)f.W * f.H * 3;
+    if (bytes < need) return fail(ctx, DSRT_EINVAL, "dsrt_readback_rgb8: need %zu bytes, got %zu", need, bytes);
+    CK(cudaSetDevice(ctx->device));
+    const int spp = total_spp < 1 ? 1 : total_spp;
+    const float g = gamma > 0.0f ? gamma : 1.0f;                   // gpu_render.cu:1043
+    launch_tonemap(f.accum, f.d_rgb, f.W, f.H, 1.0f / (float)spp, 1.0f / g, f.stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, f.d_rgb, need, cudaMemcpyDeviceToHost, f.stream));
+    if (wait) CK(cudaStreamSynchronize(f.stream));
+    return DSRT_OK;
+}
+
+}  // namespace
+
+extern "C" int dsrt_render_frame(dsrt_ctx* ctx, const DsrtCamera* camera,
+                                 const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                                 const DsrtRenderParams* params, uint64_t seed,
+                                 int sample_begin, int sample_end, const int rect[4], int keep_accum) {
+    if (!ctx) return DSRT_EINVAL;
+    if (ctx->slots[0].pending) { const int rc = finish_frame(ctx, 0); if (rc) return rc; }
+    const int rc = enqueue_frame(ctx, 0, camera, sun_dir, sun_radiance, sun_enabled, params, seed, sample_begin, sample_end, rect, keep_accum);
+    if (rc) return rc;
+    return finish_frame(ctx, 0);
+}
+
+extern "C" int dsrt_render_frame_async(dsrt_ctx* ctx, int slot, const DsrtCamera* camera,
+                                       const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                                       const DsrtRenderParams* params, uint64_t seed,
+                                       int sample_begin, int sample_end, const int rect[4], int keep_accum) {
+    if (!ctx) return DSRT_EINVAL;
+    const int rc = check_slot(ctx, slot);
+    if (rc) return rc;
+    return enqueue_frame(ctx, slot, camera, sun_dir, sun_radiance, sun_enabled, params, seed, sample_begin, sample_end, rect, keep_accum);
+}
+
+extern "C" int dsrt_readback_rgb8_async(dsrt_ctx* ctx, int slot, int total_spp, float gamma, unsigned char* dst, size_t bytes) {
+    if (!ctx || !dst) return DSRT_EINVAL;
+    const int rc = check_slot(ctx, slot);
+    if (rc) return rc;
+    return readback_rgb8_impl(ctx, slot, total_spp, gamma, dst, bytes, false);
+}
+
+extern "C" int dsrt_frame_wait(dsrt_ctx* ctx, int slot, DsrtFrameStats* out) {
+    if (!ctx) return DSRT_EINVAL;
+    int rc = check_slot(ctx, slot);
+    if (rc) return rc;
+    rc = finish_frame(ctx, slot);
+    if (rc) return rc;
+    if (out) *out = ctx->slots[slot].fstats;
     return DSRT_OK;
 }
 
 extern "C" int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out) {
     if (!ctx || !out) return DSRT_EINVAL;
-    *out = ctx->fstats;
+    *out = ctx->slots[0].fstats;
     return DSRT_OK;
 }
 
@@ -699,35 +895,40 @@ extern "C" void dsrt_host_free(void* ptr) {
 
 extern "C" int dsrt_readback_rgb8(dsrt_ctx* ctx, int total_spp, float gamma, unsigned char* dst, size_t bytes) {
     if (!ctx || !dst) return DSRT_EINVAL;
-    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
-    const size_t need = (size_t)ctx->W * ctx->H * 3;
-    if (bytes < need) return fail(ctx, DSRT_EINVAL, "dsrt_readback_rgb8: need %zu bytes, got %zu", need, bytes);
-    CK(cudaSetDevice(ctx->device));
-    const int spp = total_spp < 1 ? 1 : total_spp;
-    const float g = gamma > 0.0f ? gamma : 1.0f;                   // gpu_render.cu:1043
-    launch_tonemap(ctx->accum, ctx->d_rgb, ctx->W, ctx->H, 1.0f / (float)spp, 1.0f / g, ctx->stream);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(dst, ctx->d_rgb, need, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSRT_OK;
+    return readback_rgb8_impl(ctx, 0, total_spp, gamma, dst, bytes, true);
 }
 
 extern "C" int dsrt_readback_accum(dsrt_ctx* ctx, float* dst, size_t bytes) {
     if (!ctx || !dst) return DSRT_EINVAL;
-    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
-    const size_t need = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+    FrameSlot& f = ctx->slots[0];
+    if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)f.W * f.H * 3 * sizeof(float);
     if (bytes < need) return fail(ctx, DSRT_EINVAL, "dsrt_readback_accum: need %zu bytes, got %zu", need, bytes);
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(dst, ctx->accum, need, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(dst, f.accum, need, cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return DSRT_OK;
 }
 
 extern "C" int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_floats) {
     if (!ctx || !device_ptr || !num_floats) return DSRT_EINVAL;
-    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
-    *device_ptr = ctx->accum;
-    *num_floats = (size_t)ctx->W * ctx->H * 3;
+    FrameSlot& f = ctx->slots[0];
+    if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    *device_ptr = f.accum;
+    *num_floats = (size_t)f.W * f.H * 3;
+    return DSRT_OK;
+}
+
+extern "C" int dsrt_clear_accum(dsrt_ctx* ctx, int width, int height) {
+    if (!ctx || width < 2 || height < 2) return DSRT_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    FrameSlot& f = ctx->slots[0];
+    if (f.pending) { const int rc = finish_frame(ctx, 0); if (rc) return rc; }
+    bool fresh = false;
+    const int rc = ensure_image(ctx, f, width, height, &fresh);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(f.accum, 0, (size_t)width * height * 3 * sizeof(float), f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return DSRT_OK;
 }
 
@@ -735,7 +936,8 @@ extern "C" int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_f
 // ncclRedOp_t, int root, ncclComm_t, cudaStream_t); ncclFloat = 7, ncclSum = 0 (nccl.h, stable ABI).
 extern "C" int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root) {
     if (!ctx || !nccl_comm || root < 0) return DSRT_EINVAL;
-    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    FrameSlot& f = ctx->slots[0];
+    if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
     typedef int (*reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
     static reduce_fn fn = nullptr;
     if (!fn) {
@@ -748,8 +950,8 @@ extern "C" int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root) {
         }
     }
     CK(cudaSetDevice(ctx->device));
-    const size_t nf = (size_t)ctx->W * ctx->H * 3;
-    const int rc = fn(ctx->accum, ctx->accum, nf, /*ncclFloat*/ 7, /*ncclSum*/ 0, root, nccl_comm, ctx->stream);
+    const size_t nf = (size_t)f.W * f.H * 3;
+    const int rc = fn(f.accum, f.accum, nf, /*ncclFloat*/ 7, /*ncclSum*/ 0, root, nccl_comm, ctx->stream);
     if (rc != 0) return fail(ctx, DSRT_ECUDA, "ncclReduce failed with code %d", rc);
     CK(cudaStreamSynchronize(ctx->stream));
     return DSRT_OK;
@@ -757,11 +959,12 @@ extern "C" int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root) {
 
 extern "C" int dsrt_upload_accum(dsrt_ctx* ctx, const float* src, size_t bytes) {
     if (!ctx || !src) return DSRT_EINVAL;
-    if (!ctx->accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
-    const size_t need = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+    FrameSlot& f = ctx->slots[0];
+    if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
+    const size_t need = (size_t)f.W * f.H * 3 * sizeof(float);
     if (bytes != need) return fail(ctx, DSRT_EINVAL, "dsrt_upload_accum: need %zu bytes, got %zu", need, bytes);
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->accum, src, need, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.accum, src, need, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DSRT_OK;
 }
@@ -793,7 +996,7 @@ extern "C" int dsrt_trace_closest_device(dsrt_ctx* ctx, const void* rays_device,
     CK(cudaSetDevice(ctx->device));
     launch_trace_closest(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes, SphereSet{ctx->d_spheres, ctx->nspheres},
                          (const float4*)rays_device, n, (float4*)hits_device,
-                         ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
+                         ctx->slots[0].counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());
     return DSRT_OK;
 }
@@ -805,7 +1008,7 @@ extern "C" int dsrt_trace_occluded_device(dsrt_ctx* ctx, const void* rays_device
     CK(cudaSetDevice(ctx->device));
     launch_trace_occluded(ctx->bvh.nodes, ctx->bvh.tri_records, ctx->bvh.num_nodes, SphereSet{ctx->d_spheres, ctx->nspheres},
                           (const float4*)rays_device, n, (uint8_t*)occluded_device,
-                          ctx->counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
+                          ctx->slots[0].counters + C_FETCH, ctx->dims.trace_blocks, ctx->stream);
     CK(cudaGetLastError());
     return DSRT_OK;
 }
@@ -856,4 +1059,89 @@ extern "C" int dsrt_first_hits(dsrt_ctx* ctx, const DsrtCamera* camera, int widt
     rc = dsrt_trace_closest_device(ctx, ctx->t_rays, n, ctx->t_hits);
     if (rc) return rc;
     return download_hits(ctx, n, tri, t, u, v);
+}
+
+// The first hits of ONE sample of every pixel, taken from the pipeline's own first stage: k_tile_entries (per-tile
+// start nodes, culled tiles) and k_primary (ray generation with the estimator's jitter, traversal from the start
+// nodes), exactly as dsrt_render_frame launches them -- unlike dsrt_first_hits, which traces fixed-jitter rays from the
+// root through the generic kernel.  Also reports where each hit was found: the BVH8 node whose leaf child held the
+// triangle and the triangle's position in the leaf-ordered record array.
+extern "C" int dsrt_primary_hits(dsrt_ctx* ctx, const DsrtCamera* camera, const DsrtRenderParams* params, uint64_t seed,
+                                 int sample, int32_t* tri, float* t, float* u, float* v,
+                                 int32_t* leaf_node, int32_t* leaf_record) {
+    if (!ctx) return DSRT_EINVAL;
+    FrameArgs a;
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    int rc = check_frame_args(ctx, camera, zero3, zero3, 0, params, sample, sample + 1, nullptr, &a);
+    if (rc) return rc;
+    if (a.rng_mode == DSRT_RNG_REF_LCG && sample != 0)
+        return fail(ctx, DSRT_EINVAL, "dsrt_primary_hits: the LCG replay can only show sample 0 (later ones depend on the paths before)");
+    CK(cudaSetDevice(ctx->device));
+    FrameSlot& f = ctx->slots[0];
+    if (f.pending) { rc = finish_frame(ctx, 0); if (rc) return rc; }
+    bool fresh = false;
+    rc = ensure_image(ctx, f, a.W, a.H, &fresh);
+    if (rc) return rc;
+    f.lcg_next_sample = -1;
+    FrameConst fc;
+    fill_frame_consts(ctx, a, camera, zero3, zero3, params, seed, fc);
+    const size_t paths = (size_t)fc.slots_per_sample;
+    rc = ensure_work(ctx, f, paths);
+    if (rc) return rc;
+    rc = ensure_tiles(ctx, f, fc);
+    if (rc) return rc;
+    if (paths > f.cap_leaf) {
+        cudaFree(f.dbg_leaf); f.dbg_leaf = nullptr; f.cap_leaf = 0;
+        CK(cudaMalloc(&f.dbg_leaf, paths * sizeof(uint2)));
+        f.cap_leaf = paths;
+    }
+    bind_slot(f, fc);
+    fc.dbg_leaf = f.dbg_leaf;
+    fc.s0 = sample;
+    fc.spb = 1;
+    if (a.rng_mode == DSRT_RNG_REF_LCG) launch_lcg_seed(f.rng_pix, a.W, a.H, (uint32_t)(seed & 0xFFFFFFFFu), f.stream);
+    CK(cudaMemsetAsync(f.stats, 0, sizeof(unsigned long long) * S_COUNT, f.stream));
+    launch_tile_entries(fc, f.tile_table, f.active_tiles, f.stream);
+    launch_batch_begin(fc, f.stream);
+    launch_primary(fc, ctx->dims, true, f.stream);
+    CK(cudaGetLastError());
+    uint32_t hc[C_COUNT];
+    CK(cudaMemcpyAsync(hc, f.counters, sizeof(hc), cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
+    const size_t n = hc[C_NIN];
+    if (n > paths) return fail(ctx, DSRT_ECUDA, "dsrt_primary_hits: %zu hits for %zu paths", n, paths);
+    std::vector<float4> hh(n);
+    std::vector<uint32_t> hp(n);
+    std::vector<uint2> hl(n);
+    if (n) {
+        CK(cudaMemcpyAsync(hh.data(), f.hits, n * sizeof(float4), cudaMemcpyDeviceToHost, f.stream));
+        CK(cudaMemcpyAsync(hp.data(), f.pq, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, f.stream));
+        CK(cudaMemcpyAsync(hl.data(), f.dbg_leaf, n * sizeof(uint2), cudaMemcpyDeviceToHost, f.stream));
+        CK(cudaStreamSynchronize(f.stream));
+    }
+    const size_t px = (size_t)a.W * a.H;
+    for (size_t i = 0; i < px; ++i) {
+        if (tri) tri[i] = -1;
+        if (t) t[i] = 1e9f;
+        if (u) u[i] = 0.f;
+        if (v) v[i] = 0.f;
+        if (leaf_node) leaf_node[i] = -1;
+        if (leaf_record) leaf_record[i] = -1;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        // one sample in flight: path = slot = tile * 32 + position in the 8x4 tile (render.cu: slot_to_pixel)
+        const uint32_t slot = hp[i], tile = slot >> 5, in = slot & 31u;
+        const int x = (int)((tile % (uint32_t)fc.tiles_x) * 8u + (in & 7u)), y = (int)((tile / (uint32_t)fc.tiles_x) * 4u + (in >> 3));
+        if (x >= a.W || y >= a.H) return fail(ctx, DSRT_ECUDA, "dsrt_primary_hits: a hit outside the image");
+        const size_t o = (size_t)y * a.W + x;
+        int32_t id;
+        memcpy(&id, &hh[i].w, 4);
+        if (tri) tri[o] = id;
+        if (t) t[o] = hh[i].x;
+        if (u) u[o] = hh[i].y;
+        if (v) v[o] = hh[i].z;
+        if (leaf_node) leaf_node[o] = (int32_t)hl[i].x;
+        if (leaf_record) leaf_record[o] = (int32_t)hl[i].y;
+    }
+    return DSRT_OK;
 }

@@ -256,12 +256,15 @@ __device__ __forceinline__ uint32_t node_test(const uint4* __restrict__ nodes, u
 // The wait for a triangle record is the hottest single stall of the traversal (13 % of k_trace's
 // samples); prefetching the later records of a group into L1 and fetching two records per trip
 // were both measured slower as well (+3 %: the loop runs at the 64-register cap).
-struct LaneTrav {
+// TRACK = true (parity hook only) also records the node whose leaf child held the accepted triangle.
+template <bool TRACK>
+struct LaneTravT {
     float ox, oy, oz, dx, dy, dz;
     float idx, idy, idz;
     float tmin, tmax;             // tmax shrinks to the closest accepted hit
     float hu, hv;
     int htri;                     // position in the leaf-ordered record array, -1 = none, -2 - i = sphere i
+    uint32_t hnode;               // TRACK only: the node visited when htri was accepted
     uint32_t octinv;
     uint2 ngroup;
     uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
@@ -274,6 +277,7 @@ struct LaneTrav {
         idx = safe_rcp_dir(dx_); idy = safe_rcp_dir(dy_); idz = safe_rcp_dir(dz_);
         tmin = tmin_; tmax = tmax_;
         hu = 0.f; hv = 0.f; htri = -1;
+        if (TRACK) hnode = 0xFFFFFFFFu;
         const uint32_t oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
         octinv = 7u - oct;
         ngroup = make_uint2(0u, 0x80000000u);      // the root as a one-bit node group
@@ -284,12 +288,14 @@ struct LaneTrav {
     __device__ __forceinline__ bool step(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
                                          TravStack& stack) {
         uint2 tgroup;
+        uint32_t cur_node = 0u;
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t bit = 31u - __clz(ngroup.y);
             ngroup.y &= ~(1u << bit);
             const uint32_t slot = (bit - 24u) ^ octinv;
             const uint32_t rel = __popc(ngroup.y & 0xFFu & ((1u << slot) - 1u));
             const uint32_t node_index = ngroup.x + rel;
+            cur_node = node_index;
             if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
             uint32_t child_base, tri_base, imask, tri_hits;
             const uint32_t slots = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
@@ -311,6 +317,7 @@ struct LaneTrav {
             float t, u, v;
             if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
                 tmax = t; hu = u; hv = v; htri = (int)ti;
+                if (TRACK) hnode = cur_node;
                 if (any_hit) return true;
             }
         }
@@ -360,5 +367,6 @@ struct LaneTrav {
         }
     }
 };
+using LaneTrav = LaneTravT<false>;
 
 }  // namespace dsrt

@@ -44,8 +44,11 @@ struct FrameConst {
     float cam_o[3], cam_llc[3], cam_h[3], cam_v[3];
     int W, H;
     int x0, y0, rw, rh;               // render rectangle
-    const uint2* tile_entries;        // per 8x4-pixel tile: the node group its camera rays start from (k_tile_entries),
-                                      // y == 0: the tile cannot hit a triangle; nullptr = every ray starts at the root
+    const uint2* tile_entries;        // per 8x4-pixel tile: the node groups its camera rays start from (k_tile_entries),
+                                      // y == 0: the tile cannot hit a triangle
+    const uint32_t* active_tiles;     // the tiles whose camera rays are generated at all, compacted by k_tile_entries
+    uint32_t* n_active;               // their number (one device word per frame)
+    int tile_walk;                    // 1: k_tile_entries walks the BVH per tile; 0: every tile starts at the root
     int cull_tiles;                   // 1: a tile with no entries is skipped outright (Philox stream, no spheres)
     int cull_pixels;                  // 1: the bounds below are in force (Philox stream, no spheres, scene box in front of the camera)
     int hit_x0, hit_y0, hit_x1, hit_y1;   // pixels outside [hit_x0, hit_x1] x [hit_y0, hit_y1] cannot see the triangles:
@@ -65,6 +68,9 @@ struct FrameConst {
     float4* rq_d[2];                  // ray queue: dir.xyz, unused
     float4* hits;                     // t,u,v,bits(id) per queue entry; id = uploaded triangle index,
                                       // -1 = miss, -2 - i = sphere i
+    uint32_t* pq;                     // first hits (what k_primary leaves for the depth-0 k_shade): path of entry i of
+                                      // `hits`; the camera ray is regenerated from the path, not stored
+    uint2* dbg_leaf;                  // parity hook only: (node index, record position) of first hit i; else nullptr
     float4* st_a;                     // per path: throughput.xyz, bits(rng state / draw index)
     float4* st_b;                     // per path: L.xyz (k_resolve applies the per-sample clamp), unused
     float4* sq_o;                     // shadow queue: origin.xyz, bits(path)
@@ -76,21 +82,24 @@ struct FrameConst {
 };
 
 struct LaunchDims {
-    int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0;
+    int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0, tail_blocks = 0;
 };
+constexpr uint32_t kTailAll = 0xFFFFFFFFu;      // launch_tail threshold: finish whatever is left
 
 // Host-callable launchers (all asynchronous on `s`).
 void launch_dims(LaunchDims* d, int device);
 void launch_batch_begin(const FrameConst& fc, cudaStream_t s);
-// Fills `table` (one uint2 per 8x4-pixel tile of the render rectangle) with the node the rays of each tile start from.
-void launch_tile_entries(const FrameConst& fc, uint2* table, cudaStream_t s);
-void launch_primary(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
+// Fills `table` (kTileEntries uint2 per 8x4-pixel tile of the render rectangle) with the nodes the rays of each tile
+// start from, and fc.active_tiles / fc.n_active with the tiles that need camera rays at all (n_active zeroed first).
+void launch_tile_entries(const FrameConst& fc, uint2* table, uint32_t* active_tiles, cudaStream_t s);
+// track_leaf: the parity-hook variant that also fills fc.dbg_leaf.
+void launch_primary(const FrameConst& fc, const LaunchDims& d, bool track_leaf, cudaStream_t s);
 void launch_trace(const FrameConst& fc, int cur, int shadow_slot, const LaunchDims& d, cudaStream_t s);
 void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
 void launch_advance(const FrameConst& fc, int depth, cudaStream_t s);
 // All remaining bounces of the rays in queue `cur` (traced, not yet shaded at depth0) in one launch --
-// a no-op unless at most `threshold` rays are left.
-void launch_tail(const FrameConst& fc, int cur, int depth0, uint32_t threshold, cudaStream_t s);
+// a no-op unless at most `threshold` rays are left (kTailAll: never a no-op).
+void launch_tail(const FrameConst& fc, int cur, int depth0, uint32_t threshold, const LaunchDims& d, cudaStream_t s);
 void launch_resolve(const FrameConst& fc, const LaunchDims& d, cudaStream_t s);
 void launch_tonemap(const float* accum, unsigned char* rgb, int W, int H, float inv_spp, float inv_gamma, cudaStream_t s);
 void launch_lcg_seed(uint32_t* rng_pix, int W, int H, uint32_t seed32, cudaStream_t s);

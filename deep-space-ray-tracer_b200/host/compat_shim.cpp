@@ -52,7 +52,7 @@ extern "C" void gpu_render_scene(const DsrtLegacyScene* scene, int width, int he
     if (!ctx) return;
 
     int rc = dsrt_scene_upload_device(ctx, scene->triangles, scene->num_triangles,
-                                      scene->materials, scene->num_materials, scene->num_spheres,
+                                      scene->materials, scene->num_materials, scene->spheres, scene->num_spheres,
                                       scene->textures, scene->num_textures,
                                       scene->texture_pool, scene->texture_pool_floats);
     if (rc != DSRT_OK) { std::fprintf(stderr, "gpu_render_scene: %s\n", dsrt_last_error(ctx)); return; }

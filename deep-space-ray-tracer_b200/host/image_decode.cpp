@@ -129,6 +129,9 @@ bool decode_png(const std::vector<unsigned char>& f, DecodedImage& out) {
         prow[p] = (pw[p] * bits_pp + 7) / 8;
         if (pw[p] && ph[p]) total += (prow[p] + 1) * ph[p];
     }
+    // a deflate stream expands at most ~1032:1, so a header that promises more than the IDAT data can hold is
+    // malformed: refuse before allocating (W and H come from the file and may be anything up to 2^24 each)
+    if (total > idat.size() * 1040u + 4096u || (uint64_t)W * H > (1ull << 28)) return false;
     std::vector<unsigned char> raw(total);
     {
         uLongf dlen = (uLongf)raw.size();
@@ -252,6 +255,9 @@ bool decode_tga(const std::vector<unsigned char>& f, DecodedImage& out) {
     if (W <= 0 || H <= 0 || (gray ? bpp != 8 && bpp != 16 : bpp != 24 && bpp != 32)) return false;
     const size_t px = (size_t)bpp / 8;
     size_t pos = 18 + (size_t)idlen;
+    // the header may promise up to 65535 x 65535 pixels: check against what the file can hold before allocating
+    // (a run-length packet expands at most 128:1)
+    if (pos > f.size() || (size_t)W * H > (f.size() - pos) * (rle ? 128u : 1u)) return false;
     std::vector<unsigned char> pix((size_t)W * H * px);
     if (!rle) {
         if (pos + pix.size() > f.size()) return false;
@@ -290,15 +296,19 @@ bool decode_tga(const std::vector<unsigned char>& f, DecodedImage& out) {
 
 }  // namespace
 
-bool decode_image_file(const char* path, DecodedImage& out) {
+bool decode_image_file(const char* path, DecodedImage& out, bool* exists) {
     std::vector<unsigned char> f;
-    if (!read_file(path, f) || f.size() < 4) return false;
+    if (exists) *exists = false;
+    if (!read_file(path, f)) return false;
+    if (exists) *exists = true;
+    if (f.size() < 4) return false;
     if (f[0] == 0x89 && f[1] == 'P') return decode_png(f, out);
     if (f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return decode_pnm(f, out);
     if (f[0] == 'B' && f[1] == 'M') return decode_bmp(f, out);
     const size_t L = std::strlen(path);
-    if (L >= 4 && (!std::strcmp(path + L - 4, ".tga") || !std::strcmp(path + L - 4, ".TGA"))) return decode_tga(f, out);
-    return false;
+    // TGA has no magic number: it is tried last, on anything (its header checks reject what is not one)
+    (void)L;
+    return decode_tga(f, out);
 }
 
 }  // namespace dsrt_host

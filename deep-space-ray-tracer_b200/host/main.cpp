@@ -10,24 +10,31 @@
 // and summed with a single NCCL reduce.
 //
 // The mesh: the reference hard-codes ../../iss_model/ISS_stationary.obj (main.cpp:239) and
-// silently renders an empty scene when it is missing; here --obj <path> (default: that same
-// path) is loaded by dsrt_mesh_load_obj (OBJ + MTL + map_Kd textures, host/obj_loader.cpp), and
-// when the file cannot be opened the deterministic synthetic station stands in (the NASA model
-// is not redistributable with either tree).
+// silently renders an empty scene when it is missing.  Here --obj <path> (default: that same
+// path) is loaded by dsrt_mesh_load_obj (OBJ + MTL + map_Kd textures, host/obj_loader.cpp).
+// An --obj that was asked for and cannot be opened is an error (exit 1); the missing DEFAULT
+// path renders the reference's empty scene, with a warning.  --synthetic_tris N replaces the
+// OBJ by the deterministic synthetic station (the NASA model is not redistributable with
+// either tree).
 //
-// Runs over several GPUs use one PROCESS per GPU (forked before the first CUDA call), the same
-// model as `torchrun bench.py`.  CUDA start-up costs ~2.4 s per process on a B200 box (measured;
-// it is paid before the first kernel and is outside this library's control) and is reported
-// separately from the frame loop in --stats_json.  Each worker owns its GPU, renders frames
-// k = g, g+G, ... and writes its own files; there is no collective.
+// Several GPUs are driven from ONE process, one worker thread per GPU, each with its own
+// dsrt_ctx (round 1 forked one process per GPU: eight CUDA runtimes starting at once took
+// ~11 s on a B200 box against ~2.4 s for one; here the runtime starts once and only the
+// per-device contexts are created in parallel).  Frames are handed out dynamically from one
+// atomic counter -- late poses of the shipped sequence cost ~3x the early ones -- and each
+// worker keeps TWO frames in flight on two frame slots (dsrt_render_frame_async), so the
+// latency-bound end of frame k, its tone map and its copy to the host run under the camera
+// rays of frame k+1.  There is no collective in this mode.
 //
 // Frames are written by a writer thread per GPU (PPM, then the in-process PNG encoder that
-// replaces the reference's `magick` subprocess, main.cpp:28-36), so a GPU renders frame k+1
-// while frame k is being compressed.
+// replaces the reference's `magick` subprocess, main.cpp:28-36), so a GPU renders on
+// while finished frames are being compressed.
 //
 // Extra, optional flags (defaults reproduce the reference): --width --height --spp
 // --max_depth --seed --obj <path> --obj_scale S --synthetic_tris N --diffuse_only --gpus G
-// --shard frame|sample --frames a:b --rng philox|lcg --no_png --stats_json <file>.
+// --shard frame|sample --frames a:b --rng philox|lcg --no_png --stats_json <file>
+// --dump_accum (also writes <frame>.accum, the raw float accumulation buffer) --sync_frames
+// (one frame at a time per GPU, as round 1 did).
 #include "dsrt.h"
 
 #include <atomic>
@@ -45,8 +52,6 @@
 #include <thread>
 #include <vector>
 
-#include <sys/wait.h>
-#include <unistd.h>
 
 #ifdef DSRT_WITH_NCCL
 #include <cuda_runtime.h>
@@ -61,9 +66,10 @@ struct Options {
     std::string pose_file, out_dir = "output", stats_json, shard = "frame", rng = "philox";
     std::string obj_path = "../../iss_model/ISS_stationary.obj";      // main.cpp:239
     double obj_scale = 1.0;
-    bool upscale = false, png = true, diffuse_only = false;
+    bool upscale = false, png = true, diffuse_only = false, dump_accum = false, sync_frames = false;
+    bool obj_given = false;
     int width = 800, height = 450, spp = 1000, max_depth = 50;
-    int synthetic_tris = 1000000, gpus = 1, frame_begin = 0, frame_end = -1;
+    int synthetic_tris = -1, gpus = 1, frame_begin = 0, frame_end = -1;      // -1: no synthetic stand-in
     float vfov = 40.0f;
     unsigned long long seed = 1337ULL;        // gpu_scene_builder.cpp:583
 };
@@ -81,7 +87,9 @@ void parse_args(int argc, char** argv, Options& o) {
         else if (const char* v = next("--max_depth")) o.max_depth = std::atoi(v);
         else if (const char* v = next("--seed")) o.seed = std::strtoull(v, nullptr, 10);
         else if (const char* v = next("--synthetic_tris")) o.synthetic_tris = std::atoi(v);
-        else if (const char* v = next("--obj")) o.obj_path = v;
+        else if (const char* v = next("--obj")) { o.obj_path = v; o.obj_given = true; }
+        else if (a == "--dump_accum") o.dump_accum = true;
+        else if (a == "--sync_frames") o.sync_frames = true;
         else if (const char* v = next("--obj_scale")) o.obj_scale = std::atof(v);
         else if (a == "--diffuse_only") o.diffuse_only = true;
         else if (const char* v = next("--gpus")) o.gpus = std::atoi(v);
@@ -168,16 +176,20 @@ bool save_frame(const Options& o, size_t index, const unsigned char* rgb) {
 std::mutex g_print;
 
 // Writes finished frames on its own thread so the GPU that produced them keeps rendering.
-// Frames travel in three page-locked buffers that circulate between the render loop (acquire ->
-// read back -> push) and the writer (save -> release), so at most two frames wait to be written
-// and the producer blocks beyond that.  Created after the ctx (page-locked memory needs CUDA).
+// Frames travel in four page-locked buffers that circulate between the render loop (acquire ->
+// read back -> push; two frames are in flight per GPU) and the writer (save -> release), so at most two
+// frames wait to be written and the producer blocks beyond that.  Created after the ctx (page-locked memory needs CUDA).
 class FrameWriter {
 public:
     FrameWriter(const Options& o, std::vector<FrameResult>& results)
         : o_(o), results_(results), bytes_((size_t)o.width * o.height * 3) {
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 4; ++k) {
             void* p = nullptr;
-            if (dsrt_host_alloc(&p, bytes_) != DSRT_OK) { p = std::malloc(bytes_); pageable_.push_back(p); }
+            if (dsrt_host_alloc(&p, bytes_) != DSRT_OK) {
+                p = std::malloc(bytes_);
+                if (!p) { std::fprintf(stderr, "out of host memory for the frame buffers\n"); std::abort(); }
+                pageable_.push_back(p);
+            }
             all_.push_back((unsigned char*)p);
             free_.push_back((unsigned char*)p);
         }
@@ -246,14 +258,15 @@ private:
     std::thread th_;
 };
 
-// One GPU renders the frames jobs[k] with k % stride == offset.
-void frame_worker(int device, int label, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
-                  int offset, int stride, std::vector<FrameResult>& results, std::atomic<int>& errors, SetupTimes& times) {
+// One GPU of a frame-parallel run: takes frames from the shared counter until none are left and keeps two of
+// them in flight on two frame slots of its ctx.
+void frame_worker(int device, const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
+                  std::atomic<size_t>& next, std::vector<FrameResult>& results, std::atomic<int>& errors, SetupTimes& times) {
     dsrt_ctx* ctx = nullptr;
     auto t0 = std::chrono::high_resolution_clock::now();
     if (dsrt_create(&ctx, device) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
-        std::fprintf(stderr, "GPU %d: %s\n", label, dsrt_last_error(nullptr));
+        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(nullptr));
         ++errors;
         return;
     }
@@ -261,7 +274,7 @@ void frame_worker(int device, int label, const Options& o, const SceneData& scen
     t0 = std::chrono::high_resolution_clock::now();
     if (upload(ctx, scene) != DSRT_OK) {
         std::lock_guard<std::mutex> l(g_print);
-        std::fprintf(stderr, "GPU %d: %s\n", label, dsrt_last_error(ctx));
+        std::fprintf(stderr, "GPU %d: %s\n", device, dsrt_last_error(ctx));
         ++errors;
         dsrt_destroy(ctx);
         return;
@@ -271,38 +284,74 @@ void frame_worker(int device, int label, const Options& o, const SceneData& scen
         DsrtSceneStats st;
         dsrt_scene_stats(ctx, &st);
         std::lock_guard<std::mutex> l(g_print);
-        std::cout << "GPU " << label << " scene build time: " << st.build_ms << " ms (" << st.num_wide_nodes
+        std::cout << "GPU " << device << " scene build time: " << st.build_ms << " ms (" << st.num_wide_nodes
                   << " wide nodes, upload " << st.upload_ms << " ms)\n";
     }
     const DsrtRenderParams params = make_params(o);
     FrameWriter writer(o, results);
+    const int nslots = (o.sync_frames || o.dump_accum) ? 1 : 2;
+    struct InFlight { bool busy = false; size_t k = 0; unsigned char* rgb = nullptr; } fl[2];
+    bool first = true;
     t0 = std::chrono::high_resolution_clock::now();
-    for (size_t k = (size_t)offset; k < jobs.size(); k += (size_t)stride) {
+
+    auto retire = [&](int s) {
+        if (!fl[s].busy) return;
+        fl[s].busy = false;
+        const size_t k = fl[s].k;
+        DsrtFrameStats fs{};
+        if (dsrt_frame_wait(ctx, s, &fs) != DSRT_OK) {
+            std::lock_guard<std::mutex> l(g_print);
+            std::fprintf(stderr, "frame %zu on GPU %d: %s\n", jobs[k].index, device, dsrt_last_error(ctx));
+            ++errors;
+            writer.release(fl[s].rgb);
+            return;                         // no stale file is renamed into place
+        }
+        if (first) { times.first_frame_s = seconds_since(t0); first = false; }
+        results[k].device_ms = fs.device_ms;
+        results[k].rays = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
+        if (o.dump_accum) {
+            std::vector<float> acc((size_t)o.width * o.height * 3);
+            char name[64];
+            std::snprintf(name, sizeof(name), "/frame_%04zu.accum", jobs[k].index);
+            FILE* f = dsrt_readback_accum(ctx, acc.data(), acc.size() * sizeof(float)) == DSRT_OK ? std::fopen((o.out_dir + name).c_str(), "wb") : nullptr;
+            if (f) { std::fwrite(acc.data(), sizeof(float), acc.size(), f); std::fclose(f); } else ++errors;
+        }
+        writer.push(k, jobs[k].index, fl[s].rgb);
+        std::lock_guard<std::mutex> l(g_print);
+        char name[64];
+        std::snprintf(name, sizeof(name), "frame_%04zu.png", jobs[k].index);
+        std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << device << ", " << fs.device_ms << " ms, "
+                  << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
+    };
+
+    int s = 0;
+    for (;;) {
+        const size_t k = next.fetch_add(1);
+        if (k >= jobs.size()) break;
+        retire(s);                          // the slot's previous frame (the older of the two in flight)
         const FrameJob& j = jobs[k];
         unsigned char* rgb = writer.acquire();
         DsrtCamera cam;
         dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
-        int rc = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
-        if (rc == DSRT_OK) rc = dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb, writer.bytes());
-        if (k == (size_t)offset) times.first_frame_s = seconds_since(t0);
-        if (rc != DSRT_OK) {
-            std::lock_guard<std::mutex> l(g_print);
-            std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, label, dsrt_last_error(ctx));
-            ++errors;
-            writer.release(rgb);
-            continue;                       // no stale file is renamed into place
+        int rc = dsrt_render_frame_async(ctx, s, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, 0, o.spp, nullptr, 0);
+        if (rc == DSRT_OK) {
+            fl[s].busy = true; fl[s].k = k; fl[s].rgb = rgb;
+            rc = dsrt_readback_rgb8_async(ctx, s, o.spp, params.gamma, rgb, writer.bytes());
         }
-        DsrtFrameStats fs;
-        dsrt_frame_stats(ctx, &fs);
-        results[k].device_ms = fs.device_ms;
-        results[k].rays = (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays);
-        writer.push(k, j.index, rgb);
-        std::lock_guard<std::mutex> l(g_print);
-        char name[64];
-        std::snprintf(name, sizeof(name), "frame_%04zu.png", j.index);
-        std::cout << "Saved " << o.out_dir << "/" << name << "  [GPU " << label << ", " << fs.device_ms << " ms, "
-                  << results[k].rays / (fs.device_ms * 1e3) << " Mrays/s]\n";
+        if (rc != DSRT_OK) {
+            {
+                std::lock_guard<std::mutex> l(g_print);
+                std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, device, dsrt_last_error(ctx));
+            }
+            ++errors;
+            if (fl[s].busy) { dsrt_frame_wait(ctx, s, nullptr); fl[s].busy = false; }
+            writer.release(rgb);
+            continue;
+        }
+        if (nslots == 1) retire(s); else s ^= 1;
     }
+    retire(s);
+    retire(s ^ 1);
     writer.finish();
     times.loop_s = seconds_since(t0);
     t0 = std::chrono::high_resolution_clock::now();
@@ -310,97 +359,105 @@ void frame_worker(int device, int label, const Options& o, const SceneData& scen
     times.teardown_s = seconds_since(t0);
 }
 
-// Gives a forked worker process its own GPU: with `isolate` it sees only that device (so the CUDA
-// runtime initialises one device instead of all of them) and uses ordinal 0, otherwise it uses
-// ordinal g.  Returns the ordinal to pass to dsrt_create.
-int claim_gpu(int g, bool isolate) {
-    if (!isolate) return g;
-    std::string pick = std::to_string(g);
-    if (const char* vis = std::getenv("CUDA_VISIBLE_DEVICES")) {
-        std::vector<std::string> tok;
-        std::string cur;
-        for (const char* c = vis;; ++c) {
-            if (*c == ',' || *c == 0) { tok.push_back(cur); cur.clear(); if (*c == 0) break; }
-            else cur.push_back(*c);
-        }
-        if ((size_t)g < tok.size() && !tok[(size_t)g].empty()) pick = tok[(size_t)g];
-    }
-    setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
-    return 0;
-}
-
-bool write_all(int fd, const void* src, size_t n) {
-    size_t put = 0;
-    while (put < n) {
-        const ssize_t r = write(fd, (const char*)src + put, n - put);
-        if (r <= 0) return false;
-        put += (size_t)r;
-    }
-    return true;
-}
-bool read_all(int fd, void* dst, size_t n) {
-    size_t got = 0;
-    while (got < n) {
-        const ssize_t r = read(fd, (char*)dst + got, n - got);
-        if (r <= 0) return false;
-        got += (size_t)r;
-    }
-    return true;
-}
-
-struct Wire { size_t k; FrameResult r; };
-
 #ifdef DSRT_WITH_NCCL
-// One frame at a time, its samples split over the GPUs -- one worker process per GPU (as in the
-// frame-parallel mode, and for the same reason).  Worker g renders the global sample indices
-// [spp*g/G, spp*(g+1)/G) of every pixel; one ncclReduce(sum) of the float accumulation buffer over
-// NVLink brings the frame to worker 0, which tone-maps and writes it.  The NCCL id is created by
-// worker 0 and relayed by the parent, which itself never touches CUDA.
-int sample_worker(int g, int G, int id_fd, int out_fd, const Options& o, const SceneData& scene,
-                  const std::vector<FrameJob>& jobs, bool isolate) {
-    const int device = claim_gpu(g, isolate);
-    SetupTimes times;
+// One frame at a time, its samples split over the GPUs, one worker thread per GPU.  Worker g renders the global
+// sample indices [spp*g/G, spp*(g+1)/G) of every pixel; one ncclReduce(sum) of the float accumulation buffer over
+// NVLink brings the frame to worker 0, which tone-maps and writes it.
+// A worker whose render fails still takes part in the reduce with a zeroed buffer and flags the frame, so the
+// collective neither dead-locks nor sums a partial frame; a failing collective aborts every communicator.
+struct SampleShared {
+    std::vector<ncclComm_t> comms;
+    std::vector<std::atomic<int>> comm_ready;
+    std::vector<std::atomic<int>> frame_failed;
+    std::atomic<int> abort_all{0};
+    std::vector<std::vector<FrameResult>> per;       // [gpu][frame]
+    SampleShared(int G, size_t frames) : comms((size_t)G, nullptr), comm_ready((size_t)G), frame_failed(frames), per((size_t)G, std::vector<FrameResult>(frames)) {
+        for (auto& a : comm_ready) a = 0;
+        for (auto& a : frame_failed) a = 0;
+    }
+    void abort() {
+        if (abort_all.exchange(1)) return;
+        for (size_t g = 0; g < comms.size(); ++g)
+            if (comm_ready[g].load()) ncclCommAbort(comms[g]);
+    }
+};
+
+void sample_worker(int g, int G, const ncclUniqueId& id, SampleShared& sh, const Options& o, const SceneData& scene,
+                   const std::vector<FrameJob>& jobs, std::atomic<int>& errors, SetupTimes& times) {
     auto t0 = std::chrono::high_resolution_clock::now();
     dsrt_ctx* ctx = nullptr;
-    if (dsrt_create(&ctx, device) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(nullptr)); return 1; }
+    bool ok = dsrt_create(&ctx, g) == DSRT_OK;
+    if (!ok) { std::lock_guard<std::mutex> l(g_print); std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(nullptr)); }
     times.create_s = seconds_since(t0);
-    ncclUniqueId id;
-    if (g == 0) {
-        if (ncclGetUniqueId(&id) != ncclSuccess || !write_all(out_fd, &id, sizeof(id))) { std::fprintf(stderr, "ncclGetUniqueId failed\n"); return 1; }
-    }
-    if (!read_all(id_fd, &id, sizeof(id))) { std::fprintf(stderr, "GPU %d: no NCCL id\n", g); return 1; }
     t0 = std::chrono::high_resolution_clock::now();
-    if (upload(ctx, scene) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx)); return 1; }
-    ncclComm_t comm;
-    cudaSetDevice(device);
-    if (ncclCommInitRank(&comm, G, id, g) != ncclSuccess) { std::fprintf(stderr, "GPU %d: ncclCommInitRank failed\n", g); return 1; }
+    if (ok && upload(ctx, scene) != DSRT_OK) {
+        std::lock_guard<std::mutex> l(g_print);
+        std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx));
+        ok = false;
+    }
+    // every worker joins the communicator set-up, also one that has already failed: its peers are waiting in it
+    cudaSetDevice(g);
+    ncclComm_t comm = nullptr;
+    if (ncclCommInitRank(&comm, G, id, g) != ncclSuccess) {
+        std::lock_guard<std::mutex> l(g_print);
+        std::fprintf(stderr, "GPU %d: ncclCommInitRank failed\n", g);
+        ++errors;
+        sh.abort();
+        if (ctx) dsrt_destroy(ctx);
+        return;
+    }
+    sh.comms[(size_t)g] = comm;
+    sh.comm_ready[(size_t)g] = 1;
     times.upload_s = seconds_since(t0);
+    if (!ok) ++errors;
 
     const DsrtRenderParams params = make_params(o);
-    std::vector<FrameResult> results(jobs.size());
-    int errors = 0;
+    std::vector<FrameResult>& results = sh.per[(size_t)g];
     {
         FrameWriter writer(o, results);
         t0 = std::chrono::high_resolution_clock::now();
-        for (size_t k = 0; k < jobs.size(); ++k) {
+        for (size_t k = 0; k < jobs.size() && !sh.abort_all.load(); ++k) {
             const FrameJob& j = jobs[k];
             DsrtCamera cam;
             dsrt_camera_look_at_origin(j.cam_in_model, o.vfov, o.width, o.height, o.spp, o.max_depth, &cam);
             // global sample indices stay global: the jitter depends on s/spp (gpu_render.cu:995-996)
             const int s0 = (int)((long long)o.spp * g / G), s1 = (int)((long long)o.spp * (g + 1) / G);
-            const bool rendered = dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, s0, s1, nullptr, 0) == DSRT_OK;
-            if (!rendered) { std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, g, dsrt_last_error(ctx)); ++errors; }
+            bool rendered = ok && dsrt_render_frame(ctx, &cam, j.sun_dir, kSunRadiance, 1, &params, o.seed, s0, s1, nullptr, 0) == DSRT_OK;
             DsrtFrameStats fs{};
-            dsrt_frame_stats(ctx, &fs);
-            // every worker takes part in the reduce even after a failed render (a zero buffer), so the
-            // collective cannot dead-lock
-            if (dsrt_reduce_accum(ctx, comm, 0) != DSRT_OK) { std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx)); ++errors; break; }
+            if (rendered) dsrt_frame_stats(ctx, &fs);
+            if (!rendered) {
+                {
+                    std::lock_guard<std::mutex> l(g_print);
+                    std::fprintf(stderr, "frame %zu on GPU %d: %s\n", j.index, g, ctx ? dsrt_last_error(ctx) : "no context");
+                }
+                ++errors;
+                sh.frame_failed[k] = 1;
+                if (!ctx || dsrt_clear_accum(ctx, o.width, o.height) != DSRT_OK) { sh.abort(); break; }
+            }
+            if (dsrt_reduce_accum(ctx, comm, 0) != DSRT_OK) {
+                if (!sh.abort_all.load()) {
+                    std::lock_guard<std::mutex> l(g_print);
+                    std::fprintf(stderr, "GPU %d: %s\n", g, dsrt_last_error(ctx));
+                }
+                ++errors;
+                sh.abort();
+                break;
+            }
             results[k].device_ms = rendered ? fs.device_ms : 0.0;
             results[k].rays = rendered ? (double)(fs.primary_rays + fs.bounce_rays + fs.shadow_rays) : 0.0;
             if (g == 0) {
+                if (sh.frame_failed[k].load()) continue;             // a shard is missing: no file for this frame
+                if (o.dump_accum) {
+                    std::vector<float> acc((size_t)o.width * o.height * 3);
+                    char name[64];
+                    std::snprintf(name, sizeof(name), "/frame_%04zu.accum", j.index);
+                    FILE* f = dsrt_readback_accum(ctx, acc.data(), acc.size() * sizeof(float)) == DSRT_OK ? std::fopen((o.out_dir + name).c_str(), "wb") : nullptr;
+                    if (f) { std::fwrite(acc.data(), sizeof(float), acc.size(), f); std::fclose(f); } else ++errors;
+                }
                 unsigned char* rgb = writer.acquire();
                 if (dsrt_readback_rgb8(ctx, o.spp, params.gamma, rgb, writer.bytes()) != DSRT_OK) { writer.release(rgb); ++errors; continue; }
                 writer.push(k, j.index, rgb);
+                std::lock_guard<std::mutex> l(g_print);
                 std::cout << "Saved frame " << j.index << "  [" << G << " GPUs sample-sharded, GPU 0: " << fs.device_ms << " ms]\n";
             } else {
                 results[k].done = rendered;
@@ -411,70 +468,33 @@ int sample_worker(int g, int G, int id_fd, int out_fd, const Options& o, const S
         times.loop_s = seconds_since(t0);
     }
     t0 = std::chrono::high_resolution_clock::now();
-    ncclCommDestroy(comm);
-    dsrt_destroy(ctx);
+    if (!sh.abort_all.load()) ncclCommDestroy(comm);
+    if (ctx) dsrt_destroy(ctx);
     times.teardown_s = seconds_since(t0);
-    std::cout.flush();
-    bool ok = write_all(out_fd, &times, sizeof(times));
-    for (size_t k = 0; k < jobs.size() && ok; ++k) {
-        const Wire w{k, results[k]};
-        ok = write_all(out_fd, &w, sizeof(w));
-    }
-    return (errors || !ok) ? 1 : 0;
 }
 
 int sample_sharded(const Options& o, const SceneData& scene, const std::vector<FrameJob>& jobs,
-                   std::vector<FrameResult>& results, std::vector<SetupTimes>& times, bool isolate) {
+                   std::vector<FrameResult>& results, std::vector<SetupTimes>& times) {
     const int G = o.gpus;
-    std::cout.flush();
-    std::fflush(stdout);
-    std::vector<pid_t> pids((size_t)G, -1);
-    std::vector<int> to_child((size_t)G, -1), from_child((size_t)G, -1);
-    for (int g = 0; g < G; ++g) {
-        int down[2], up[2];
-        if (pipe(down) != 0 || pipe(up) != 0) { std::perror("pipe"); return 1; }
-        const pid_t pid = fork();
-        if (pid < 0) { std::perror("fork"); return 1; }
-        if (pid == 0) {
-            close(down[1]); close(up[0]);
-            for (int q = 0; q < g; ++q) { close(to_child[(size_t)q]); close(from_child[(size_t)q]); }
-            const int rc = sample_worker(g, G, down[0], up[1], o, scene, jobs, isolate);
-            close(up[1]);
-            _exit(rc);
-        }
-        close(down[0]); close(up[1]);
-        pids[(size_t)g] = pid; to_child[(size_t)g] = down[1]; from_child[(size_t)g] = up[0];
-    }
-    int errors = 0;
     ncclUniqueId id;
-    if (read_all(from_child[0], &id, sizeof(id))) {
-        for (int g = 0; g < G; ++g) if (!write_all(to_child[(size_t)g], &id, sizeof(id))) ++errors;
-    } else {
-        ++errors;
-    }
-    for (int g = 0; g < G; ++g) close(to_child[(size_t)g]);       // a worker waiting for an id that never comes sees EOF
-    std::vector<std::vector<FrameResult>> per((size_t)G, std::vector<FrameResult>(jobs.size()));
-    for (int g = 0; g < G; ++g) {
-        if (!read_all(from_child[(size_t)g], &times[(size_t)g], sizeof(SetupTimes))) ++errors;
-        Wire w;
-        while (read_all(from_child[(size_t)g], &w, sizeof(w)))
-            if (w.k < jobs.size()) per[(size_t)g][w.k] = w.r;
-        close(from_child[(size_t)g]);
-        int status = 0;
-        waitpid(pids[(size_t)g], &status, 0);
-        if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ++errors;
-    }
+    if (ncclGetUniqueId(&id) != ncclSuccess) { std::fprintf(stderr, "ncclGetUniqueId failed\n"); return 1; }
+    SampleShared sh(G, jobs.size());
+    std::atomic<int> errors(0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] { sample_worker(g, G, id, sh, o, scene, jobs, errors, times[(size_t)g]); });
+    for (auto& t : th) t.join();
     for (size_t k = 0; k < jobs.size(); ++k) {
-        bool done = true;
+        bool done = !sh.frame_failed[k].load();
         double mx = 0, total = 0;
         for (int g = 0; g < G; ++g) {
-            done = done && per[(size_t)g][k].done;
-            mx = std::max(mx, per[(size_t)g][k].device_ms);
-            total += per[(size_t)g][k].rays;
+            done = done && sh.per[(size_t)g][k].done;
+            mx = std::max(mx, sh.per[(size_t)g][k].device_ms);
+            total += sh.per[(size_t)g][k].rays;
         }
         results[k].done = done; results[k].device_ms = mx; results[k].rays = total;
     }
-    return errors ? 1 : 0;
+    return errors.load() ? 1 : 0;
 }
 #endif
 
@@ -497,7 +517,15 @@ int main(int argc, char** argv) {
     std::string scene_desc;
     {
         dsrt_mesh* mesh = nullptr;
-        if (dsrt_mesh_load_obj(o.obj_path.c_str(), o.obj_scale, &mesh) == DSRT_OK) {
+        if (o.synthetic_tris >= 0) {
+            scene.tris.resize((size_t)o.synthetic_tris);
+            scene.mats.resize(32);
+            const int nm = dsrt_synth_mesh((int)scene.tris.size(), 1337u, o.diffuse_only ? 1 : 0, scene.tris.data(),
+                                           scene.mats.data(), (int)scene.mats.size());
+            if (nm < 0) { std::fprintf(stderr, "synthetic mesh generation failed\n"); return 1; }
+            scene.mats.resize((size_t)nm);
+            scene_desc = std::to_string(scene.tris.size()) + " synthetic triangles (--synthetic_tris)";
+        } else if (dsrt_mesh_load_obj(o.obj_path.c_str(), o.obj_scale, &mesh) == DSRT_OK) {
             DsrtMeshView v;
             dsrt_mesh_view(mesh, &v);
             scene.tris.assign(v.triangles, v.triangles + v.num_triangles);
@@ -507,15 +535,24 @@ int main(int argc, char** argv) {
             scene_desc = std::to_string(v.num_triangles) + " triangles, " + std::to_string(v.num_materials) + " materials, " +
                          std::to_string(v.num_textures) + " textures from " + o.obj_path;
             if (v.skipped_faces) scene_desc += " (" + std::to_string(v.skipped_faces) + " triangles with bad indices dropped)";
+            if (v.textures_unsupported) {
+                // the reference decodes map_Kd files with stb_image (JPEG, GIF, PSD ... as well); a texture that exists
+                // but that this loader cannot decode would silently change the picture, so it is an error, not a white
+                // stand-in (a MISSING file is white in the reference too)
+                std::fprintf(stderr, "%d texture file(s) of %s exist but could not be decoded (supported: PNG, PNM, BMP, TGA); "
+                                     "convert them, or set DSRT_ALLOW_MISSING_TEXTURES=1 to render them white\n",
+                             v.textures_unsupported, o.obj_path.c_str());
+                if (!std::getenv("DSRT_ALLOW_MISSING_TEXTURES")) { dsrt_mesh_free(mesh); return 1; }
+            }
             dsrt_mesh_free(mesh);
+        } else if (o.obj_given) {
+            std::fprintf(stderr, "cannot open OBJ %s\n", o.obj_path.c_str());
+            return 1;
         } else {
-            scene.tris.resize((size_t)std::max(0, o.synthetic_tris));
-            scene.mats.resize(32);
-            const int nm = dsrt_synth_mesh((int)scene.tris.size(), 1337u, o.diffuse_only ? 1 : 0, scene.tris.data(),
-                                           scene.mats.data(), (int)scene.mats.size());
-            if (nm < 0) { std::fprintf(stderr, "synthetic mesh generation failed\n"); return 1; }
-            scene.mats.resize((size_t)nm);
-            scene_desc = o.obj_path + " not found: " + std::to_string(scene.tris.size()) + " synthetic triangles";
+            // the reference's behaviour for its hard-coded path (triangle_mesh.h:172-173): an empty mesh, black frames
+            std::fprintf(stderr, "WARNING: %s not found: rendering an EMPTY scene as the reference does "
+                                 "(give --obj <path>, or --synthetic_tris N for the synthetic station)\n", o.obj_path.c_str());
+            scene_desc = o.obj_path + " not found: empty scene";
         }
     }
     const auto t2 = clk::now();
@@ -564,60 +601,24 @@ int main(int argc, char** argv) {
     int rc = 0;
     const int G = std::max(1, o.gpus);
     std::vector<SetupTimes> times((size_t)G);
-    // DSRT_CLI_ISOLATE=1 hides the other GPUs from each worker process.  Off by default: measured on B200 boxes it
-    // does not shorten CUDA start-up (2.4 s vs 3.6 s per process at 2 GPUs) and slows NCCL's set-up.
-    const bool isolate = std::getenv("DSRT_CLI_ISOLATE") && std::atoi(std::getenv("DSRT_CLI_ISOLATE")) != 0;
     const auto render_start = clk::now();
     if (o.shard == "sample" && G > 1) {
 #ifdef DSRT_WITH_NCCL
-        rc = sample_sharded(o, scene, jobs, results, times, isolate);
+        rc = sample_sharded(o, scene, jobs, results, times);
 #else
         std::fprintf(stderr, "--shard sample needs a build with NCCL\n");
         rc = 1;
 #endif
     } else {
         std::atomic<int> errors(0);
+        std::atomic<size_t> next(0);
         if (G == 1) {
-            frame_worker(0, 0, o, scene, jobs, 0, 1, results, errors, times[0]);
+            frame_worker(0, o, scene, jobs, next, results, errors, times[0]);
         } else {
-            // one worker process per GPU; results come back through a pipe
-            std::cout.flush();
-            std::fflush(stdout);
-            std::vector<pid_t> pids((size_t)G, -1);
-            std::vector<int> rfd((size_t)G, -1);
-            for (int g = 0; g < G; ++g) {
-                int fd[2];
-                if (pipe(fd) != 0) { std::perror("pipe"); return 1; }
-                const pid_t pid = fork();
-                if (pid < 0) { std::perror("fork"); return 1; }
-                if (pid == 0) {
-                    close(fd[0]);
-                    for (int q = 0; q < g; ++q) close(rfd[(size_t)q]);
-                    const int device = claim_gpu(g, isolate);
-                    frame_worker(device, g, o, scene, jobs, g, G, results, errors, times[(size_t)g]);
-                    std::cout.flush();
-                    bool ok = write_all(fd[1], &times[(size_t)g], sizeof(SetupTimes));
-                    for (size_t k = (size_t)g; k < jobs.size() && ok; k += (size_t)G) {
-                        const Wire w{k, results[k]};
-                        ok = write_all(fd[1], &w, sizeof(w));
-                    }
-                    close(fd[1]);
-                    _exit((errors || !ok) ? 1 : 0);
-                }
-                close(fd[1]);
-                pids[(size_t)g] = pid;
-                rfd[(size_t)g] = fd[0];
-            }
-            for (int g = 0; g < G; ++g) {
-                if (!read_all(rfd[(size_t)g], &times[(size_t)g], sizeof(SetupTimes))) ++errors;
-                Wire w;
-                while (read_all(rfd[(size_t)g], &w, sizeof(w)))
-                    if (w.k < results.size()) results[w.k] = w.r;
-                close(rfd[(size_t)g]);
-                int status = 0;
-                waitpid(pids[(size_t)g], &status, 0);
-                if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ++errors;
-            }
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; ++g)
+                th.emplace_back([&, g] { frame_worker(g, o, scene, jobs, next, results, errors, times[(size_t)g]); });
+            for (auto& t : th) t.join();
         }
         rc = errors ? 1 : 0;
     }

@@ -38,6 +38,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -213,15 +215,14 @@ struct dsrt_mesh {
     std::vector<DsrtTextureHeader> tex;
     std::vector<float> pool;
     std::vector<std::string> tex_paths;
-    int nverts = 0, nuvs = 0, skipped = 0, tex_failed = 0, flipped = 0;
+    int nverts = 0, nuvs = 0, skipped = 0, tex_failed = 0, tex_unsupported = 0, flipped = 0;
 };
 
-extern "C" int dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh** out) {
-    if (!obj_path || !out) return DSRT_EINVAL;
-    *out = nullptr;
+static int mesh_load_obj_impl(const char* obj_path, double scale, dsrt_mesh** out, std::unique_ptr<dsrt_mesh>& holder) {
     std::ifstream in(obj_path);
     if (!in) return DSRT_EIO;
-    dsrt_mesh* M = new dsrt_mesh();
+    holder.reset(new dsrt_mesh());
+    dsrt_mesh* M = holder.get();
 
     const std::string path(obj_path);
     const size_t slash = path.find_last_of("/\\");
@@ -355,9 +356,11 @@ extern "C" int dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh*
     for (const std::string& tp : M->tex_paths) {
         dsrt_host::DecodedImage img;
         DsrtTextureHeader h;
-        if (!dsrt_host::decode_image_file(tp.c_str(), img)) {
-            std::fprintf(stderr, "WARN: failed to load texture '%s'\n", tp.c_str());
+        bool exists = false;
+        if (!dsrt_host::decode_image_file(tp.c_str(), img, &exists)) {
+            std::fprintf(stderr, "WARN: failed to load texture '%s'%s\n", tp.c_str(), exists ? " (the file exists but is in a format this loader does not decode)" : "");
             ++M->tex_failed;
+            if (exists) ++M->tex_unsupported;
             h.width = 1; h.height = 1; h.offset = float_offset;
             M->pool.insert(M->pool.end(), {1.0f, 1.0f, 1.0f});
             float_offset += 3;
@@ -378,8 +381,22 @@ extern "C" int dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh*
         M->tris[i].albedo_tex = tri_tex_ref[i];
         M->mats[(size_t)M->tris[i].material_id].albedo = DsrtVec3{1.0f, 1.0f, 1.0f};      // :275-278
     }
-    *out = M;
+    *out = holder.release();
     return DSRT_OK;
+}
+
+// No exception crosses the C ABI: a malformed or huge file ends as an error code.
+extern "C" int dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh** out) {
+    if (!obj_path || !out) return DSRT_EINVAL;
+    *out = nullptr;
+    std::unique_ptr<dsrt_mesh> holder;
+    try {
+        return mesh_load_obj_impl(obj_path, scale, out, holder);
+    } catch (const std::bad_alloc&) {
+        return DSRT_ENOMEM;
+    } catch (...) {
+        return DSRT_EIO;
+    }
 }
 
 extern "C" int dsrt_mesh_view(const dsrt_mesh* m, DsrtMeshView* v) {
@@ -390,6 +407,7 @@ extern "C" int dsrt_mesh_view(const dsrt_mesh* m, DsrtMeshView* v) {
     v->texture_pool = m->pool.data(); v->texture_pool_floats = (int)m->pool.size();
     v->num_vertices = m->nverts; v->num_uvs = m->nuvs;
     v->skipped_faces = m->skipped; v->textures_failed = m->tex_failed; v->textures_flipped = m->flipped;
+    v->textures_unsupported = m->tex_unsupported;
     return DSRT_OK;
 }
 

@@ -33,7 +33,7 @@ extern "C" {
 #define DSRT_EINVAL       -1   /* bad argument */
 #define DSRT_ECUDA        -2   /* a CUDA runtime call failed */
 #define DSRT_ENOSCENE     -3   /* render/trace before dsrt_scene_upload */
-#define DSRT_EUNSUPPORTED -4   /* combination not supported (spheres through the device-pointer upload) */
+#define DSRT_EUNSUPPORTED -4   /* not available in this build / on this box (libnccl missing) */
 #define DSRT_EIO          -5   /* file could not be read/written */
 #define DSRT_ENOMEM       -6
 
@@ -66,11 +66,14 @@ int dsrt_scene_upload(dsrt_ctx* ctx,
                       const DsrtTextureHeader* textures, int ntextures,
                       const float* texture_pool, int texture_pool_floats);
 /* Same, from arrays that already live in the memory of ctx's GPU (what the reference's
- * GPUScene holds after its own build_gpu_scene): the triangle array is consumed in place,
- * no host round trip.  Material ids are not range-checked on this path. */
+ * GPUScene holds after its own build_gpu_scene, inc/gpu_scene.h:116-173): the triangle array is
+ * consumed in place, no host round trip; material ids are range-checked by a kernel.  The few
+ * spheres (and the material table, to find the emissive ones) are read back and packed on the
+ * host as in dsrt_scene_upload. */
 int dsrt_scene_upload_device(dsrt_ctx* ctx,
                              const DsrtTriangle* tris_device, int ntris,
-                             const DsrtMaterial* mats_device, int nmats, int nspheres,
+                             const DsrtMaterial* mats_device, int nmats,
+                             const DsrtSphere* spheres_device, int nspheres,
                              const DsrtTextureHeader* textures_device, int ntextures,
                              const float* texture_pool_device, int texture_pool_floats);
 int dsrt_scene_stats(dsrt_ctx* ctx, DsrtSceneStats* out);
@@ -95,6 +98,29 @@ int dsrt_render_frame(dsrt_ctx* ctx,
                       int sample_begin, int sample_end,
                       const int rect[4], int keep_accum);
 int dsrt_frame_stats(dsrt_ctx* ctx, DsrtFrameStats* out);
+
+/* The same frame call without the wait.  A ctx has DSRT_MAX_SLOTS frame slots, each with its own
+ * stream, image buffers and work memory (allocated at first use); dsrt_render_frame is slot 0
+ * followed by a wait.  A frame enqueued here runs asynchronously; the host never synchronises
+ * inside a frame (queue sizes live in device memory and the launch sequence is fixed), so a caller
+ * that alternates two slots keeps the GPU busy across frames: the latency-bound end of frame k
+ * (few rays left, tone map, copy to the host) runs under the camera rays of frame k+1.  The host
+ * arguments are consumed before the call returns.  dsrt_readback_rgb8_async enqueues the tone map
+ * and the copy of the slot's frame to `dst` behind it (dst should be page-locked, dsrt_host_alloc,
+ * for the copy to be asynchronous; it must stay valid until dsrt_frame_wait).  dsrt_frame_wait
+ * blocks until everything enqueued on the slot is done and returns the frame's statistics (out
+ * may be NULL).  A slot takes one frame at a time: enqueueing on a slot that has not been waited
+ * for is DSRT_EINVAL.  The reference has no counterpart: it is synchronous and re-uploads the
+ * scene per frame (src/main.cpp:404-428, src/gpu_render.cu:1052-1097). */
+#define DSRT_MAX_SLOTS 4
+int dsrt_render_frame_async(dsrt_ctx* ctx, int slot,
+                            const DsrtCamera* camera,
+                            const float sun_dir[3], const float sun_radiance[3], int sun_enabled,
+                            const DsrtRenderParams* params, uint64_t seed,
+                            int sample_begin, int sample_end,
+                            const int rect[4], int keep_accum);
+int dsrt_readback_rgb8_async(dsrt_ctx* ctx, int slot, int total_spp, float gamma, unsigned char* dst, size_t bytes);
+int dsrt_frame_wait(dsrt_ctx* ctx, int slot, DsrtFrameStats* out);
 /* 1 = time the traversal / shading kernels separately with CUDA events (adds launches of
  * event records only; default 0). */
 int dsrt_set_stage_timing(dsrt_ctx* ctx, int enabled);
@@ -141,6 +167,10 @@ int dsrt_accum_device(dsrt_ctx* ctx, void** device_ptr, size_t* num_floats);
  * looked up at the first call (dlopen), so the library itself does not depend on it;
  * DSRT_EUNSUPPORTED when it cannot be found. */
 int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root);
+/* Makes the accumulation buffer exist at width x height and zeroes it: what a rank whose
+ * dsrt_render_frame failed does before it still takes part in dsrt_reduce_accum, so that the
+ * collective neither dead-locks nor sums a partial frame. */
+int dsrt_clear_accum(dsrt_ctx* ctx, int width, int height);
 /* Replace the accumulation buffer contents from host memory (root of a host-side reduce). */
 int dsrt_upload_accum(dsrt_ctx* ctx, const float* src, size_t bytes);
 
@@ -157,6 +187,17 @@ int dsrt_trace_occluded(dsrt_ctx* ctx, const float* rays, int n, uint8_t* occlud
  * x + y*W with y = 0 the bottom row. */
 int dsrt_first_hits(dsrt_ctx* ctx, const DsrtCamera* camera, int width, int height,
                     float jx, float jy, int32_t* tri, float* t, float* u, float* v);
+/* The first hits of global sample `sample` of every pixel as the render pipeline itself finds
+ * them: the per-tile start nodes and tile culling of k_tile_entries and the fused ray generation +
+ * traversal of k_primary, with the estimator's own jitter for params->rng_mode (gpu_render.cu:
+ * 990-998; the LCG replay can show sample 0 only).  Outputs are W*H (from params), index x + y*W
+ * with y = 0 the bottom row; a pixel without a hit has tri = -1, t = 1e9.  leaf_node / leaf_record
+ * (may be NULL) say where the hit was found: the index of the 8-wide BVH node whose leaf child held
+ * the triangle, and the triangle's position in the leaf-ordered record array (see
+ * dsrt_scene_download) -- north_star's "(triangle index, BVH leaf)". */
+int dsrt_primary_hits(dsrt_ctx* ctx, const DsrtCamera* camera, const DsrtRenderParams* params, uint64_t seed,
+                      int sample, int32_t* tri, float* t, float* u, float* v,
+                      int32_t* leaf_node, int32_t* leaf_record);
 /* Device-resident closest-hit / any-hit over rays already in device memory (bench of the
  * traversal kernel alone).  rays_device: n x 8 floats; hits_device: n x 4 floats
  * {t,u,v,bits(tri)}; occluded_device: n bytes. */
@@ -189,9 +230,10 @@ int dsrt_synth_mesh(int ntris, uint32_t seed, int diffuse_only,
  * (src/gpu_scene_builder.cpp:72-138, 199-282, 518-551: material table by first use, texture
  * registry, sRGB -> linear float pool).  `scale` multiplies the vertex positions in double, as
  * triangle_mesh's constructor argument does.  Returns DSRT_EIO when the OBJ cannot be opened
- * (the reference silently continues with an empty mesh).  Texture files are decoded in-process
- * (PNG, binary PNM, BMP, TGA); an undecodable file becomes a 1x1 white texture, the
- * reference's own failure path. */
+ * (the reference silently continues with an empty mesh), DSRT_ENOMEM / DSRT_EIO when the file is
+ * too large or malformed (no exception crosses this boundary).  Texture files are decoded
+ * in-process (PNG, binary PNM, BMP, TGA); a missing or undecodable file becomes a 1x1 white
+ * texture, the reference's own failure path, and is counted in the view. */
 typedef struct dsrt_mesh dsrt_mesh;
 typedef struct DsrtMeshView {
     const DsrtTriangle*      triangles;      int32_t num_triangles;
@@ -202,6 +244,9 @@ typedef struct DsrtMeshView {
     int32_t skipped_faces;                   /* triangles dropped for an out-of-range vertex index */
     int32_t textures_failed;                 /* textures replaced by 1x1 white */
     int32_t textures_flipped;                /* 1 = pool rows are bottom-up (inc/texture.h:133 side effect) */
+    int32_t textures_unsupported;            /* of textures_failed: the file exists but is in a format this loader does
+                                                not decode (the reference's stb_image also reads JPEG, GIF, PSD, HDR):
+                                                the picture WOULD differ from the reference's; the CLI refuses to render */
 } DsrtMeshView;
 int  dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh** out);
 int  dsrt_mesh_view(const dsrt_mesh* mesh, DsrtMeshView* view);     /* pointers valid until dsrt_mesh_free */

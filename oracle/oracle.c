@@ -674,6 +674,45 @@ void or_first_hits(const OrScene* s, const float cam12[12], int W, int H, float 
     or_parallel_for(H, first_hit_row, &J);
 }
 
+/* First hit of ONE sample of every pixel with the jitter the estimator really uses
+ * (gpu_render.cu:990-998): rng_mode 1 = the reference LCG, sample 0 only (state = pixel ^ seed32,
+ * :990); rng_mode 0 = the product's Philox stream, any sample (counter (pixel, sample, 0, 0)).
+ * The pipeline's own first-hit kernel is checked against this (tests/test_gpu_parity.py). */
+typedef struct {
+    const OrScene* s; const float* cam12; int W, H, spp, sample, rng_mode; uint64_t seed;
+    int32_t* tri; float *t, *u, *v;
+} PrimaryHitJob;
+
+static void primary_hit_row(int y, void* arg) {
+    PrimaryHitJob* J = (PrimaryHitJob*)arg;
+    for (int x = 0; x < J->W; ++x) {
+        Rng rng;
+        memset(&rng, 0, sizeof(rng));
+        rng.mode = J->rng_mode;
+        rng.pixel = (uint32_t)(x + y * J->W);
+        rng.sample = (uint32_t)J->sample;
+        rng.k0 = (uint32_t)(J->seed & 0xFFFFFFFFu);
+        rng.k1 = (uint32_t)(J->seed >> 32);
+        if (J->rng_mode == 1) rng.state = rng.pixel ^ (uint32_t)(J->seed & 0xFFFFFFFFu);
+        const float jx = ((float)J->sample + rand01(&rng)) / (float)J->spp;
+        const float jy = ((float)J->sample + rand01(&rng)) / (float)J->spp;
+        Ray r = camera_ray(J->cam12, x, y, J->W, J->H, jx, jy);
+        Hit rec;
+        int hit = scene_hit_ctx(J->s, &r, 0.001f, 1e9f, 1, &rec);
+        int i = x + y * J->W;
+        J->tri[i] = hit ? (rec.sphere_index >= 0 ? -2 - rec.sphere_index : rec.tri_index) : -1;
+        J->t[i] = hit ? rec.t : 1e9f;
+        J->u[i] = hit ? rec.u : 0.f;
+        J->v[i] = hit ? rec.v : 0.f;
+    }
+}
+
+void or_primary_hits(const OrScene* s, const float cam12[12], int W, int H, int spp_total, int sample,
+                     uint64_t seed, int rng_mode, int32_t* tri, float* t, float* u, float* v) {
+    PrimaryHitJob J = {s, cam12, W, H, spp_total < 1 ? 1 : spp_total, sample, rng_mode, seed, tri, t, u, v};
+    or_parallel_for(H, primary_hit_row, &J);
+}
+
 #define OR_CHUNK 1024
 typedef struct {
     const OrScene* s; const float* rays; int n;

@@ -40,6 +40,10 @@ int      or_scene_max_leaf(const OrScene* s);
 /* cam12 = origin, lower_left_corner, horizontal, vertical (GPUCamera fields the kernel reads). */
 void or_first_hits(const OrScene* s, const float cam12[12], int W, int H, float jx, float jy,
                    int32_t* tri, float* t, float* u, float* v);
+/* First hit of sample `sample` of every pixel under the estimator's own jitter (gpu_render.cu:990-998):
+ * rng_mode 1 = reference LCG (sample 0 only), 0 = the product's Philox stream. */
+void or_primary_hits(const OrScene* s, const float cam12[12], int W, int H, int spp_total, int sample,
+                     uint64_t seed, int rng_mode, int32_t* tri, float* t, float* u, float* v);
 /* rays: n x {ox,oy,oz,tmin,dx,dy,dz,tmax}; closest hit through scene_hit (gpu_render.cu:509-551). */
 void or_trace(const OrScene* s, const float* rays, int n, int32_t* tri, float* t, float* u, float* v);
 void or_occluded(const OrScene* s, const float* rays, int n, uint8_t* occluded);

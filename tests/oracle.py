@@ -33,6 +33,8 @@ def lib():
         L.or_scene_max_leaf.argtypes = [vp]
         L.or_first_hits.argtypes = [vp, vp, i, i, f, f, vp, vp, vp, vp]
         L.or_first_hits.restype = None
+        L.or_primary_hits.argtypes = [vp, vp, i, i, i, i, C.c_uint64, i, vp, vp, vp, vp]
+        L.or_primary_hits.restype = None
         L.or_trace.argtypes = [vp, vp, i, vp, vp, vp, vp]
         L.or_trace.restype = None
         L.or_occluded.argtypes = [vp, vp, i, vp]
@@ -119,6 +121,17 @@ class Scene:
         tri = np.empty(n, np.int32)
         t, u, v = (np.empty(n, np.float32) for _ in range(3))
         lib().or_first_hits(self.h, c.ctypes.data, W, H, jx, jy, tri.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data)
+        return tri, t, u, v
+
+    def primary_hits(self, cam12, W, H, spp, sample=0, seed=1337, rng_mode=0):
+        """First hit of sample `sample` of every pixel under the estimator's jitter (rng_mode 1: LCG, sample 0 only)."""
+        assert rng_mode == 0 or sample == 0
+        n = W * H
+        c = np.ascontiguousarray(cam12, np.float32)
+        tri = np.empty(n, np.int32)
+        t, u, v = (np.empty(n, np.float32) for _ in range(3))
+        lib().or_primary_hits(self.h, c.ctypes.data, W, H, spp, sample, seed, rng_mode,
+                              tri.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data)
         return tri, t, u, v
 
     def trace(self, rays):

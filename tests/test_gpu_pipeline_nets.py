@@ -1,0 +1,327 @@
+"""Parity nets around the PRODUCTION pipeline stages (round-2 additions).
+
+* first hits dumped from k_tile_entries + k_primary themselves (per-tile start nodes, tile and pixel
+  culling, the estimator's jitter) -- bit-exact against the oracle, with the BVH leaf each hit was
+  found in (north_star: "primary-ray first hits (triangle index, BVH leaf) must match bit-exact");
+* BASELINE config 2 size (1M triangles, 1920x1080): the LCG-replay frame byte-identical to the live
+  reference kernel, first hits of the production kernel against the oracle, a Philox frame against it;
+* the legacy boundary `gpu_render_scene(const GPUScene&, int, int)` with real geometry: the
+  reference's unmodified main.cpp linked against libdsrt.so (oracle/_ref/ray_tracer_dropin,
+  ray_tracer_binding) writes the same bytes as the reference's own kernel;
+* two GPUs (skipped on a one-GPU box): frame-parallel files byte-identical to one GPU, the
+  sample-sharded frame (one NCCL reduce) allclose 1e-5 in the accumulation and identical in RGB8;
+* the asynchronous frame call: two frames in flight on two slots give the bytes of the synchronous call.
+"""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import refgpu
+from conftest import bits, cam12_of
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_DIR = ROOT / "oracle" / "_ref"
+CLI = ROOT / "deep-space-ray-tracer_b200" / "ray_tracer"
+OBJ_DIR = ROOT / "tests" / "golden" / "obj"
+DEPTH = 10
+
+
+def gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except (OSError, subprocess.SubprocessError):
+        return 0
+
+
+def leaf_tables(nodes, recs):
+    """From the downloaded BVH8 (96-byte nodes as 24 uint32, csrc/bvh8.cuh): per node the
+    [first, last) record range of each leaf slot, and per record its uploaded triangle index."""
+    imask = nodes[:, 3] >> 24
+    tri_base = nodes[:, 5].astype(np.int64)
+    meta = np.stack([(nodes[:, 6 + (s >> 2)] >> (8 * (s & 3))) & 0xFF for s in range(8)], 1).astype(np.int64)
+    is_leaf = (meta != 0) & (((imask[:, None] >> np.arange(8)[None, :]) & 1) == 0)
+    count = np.where(is_leaf, np.array([0, 1, 0, 2, 0, 0, 0, 3])[(meta >> 5) & 7], 0)
+    first = tri_base[:, None] + (meta & 31)
+    return first, first + count, is_leaf, recs[:, 3].copy().view(np.int32)
+
+
+def assert_primary_hits(ours, ref, leaf, min_hits):
+    tri, t, u, v, node, rec = ours
+    rtri, rt, ru, rv = ref
+    same = tri == rtri
+    # the only legitimate index difference is an exact-t tie resolved by traversal order (SURVEY A-8)
+    tie = (~same) & (tri >= 0) & (rtri >= 0) & (bits(t) == bits(rt))
+    assert (same | tie).all(), f"{(~(same | tie)).sum()} first hits differ: pixels {np.nonzero(~(same | tie))[0][:8]}"
+    hit = same & (rtri >= 0)
+    assert hit.sum() >= min_hits, hit.sum()
+    assert np.array_equal(bits(t)[hit], bits(rt)[hit])
+    assert np.array_equal(bits(u)[hit], bits(ru)[hit]) and np.array_equal(bits(v)[hit], bits(rv)[hit])
+    # the BVH leaf: the reported node has a leaf slot whose record range holds the reported record,
+    # and that record is the reported triangle
+    first, last, is_leaf, rec_tri = leaf
+    h = tri >= 0
+    assert (node[~h] == -1).all() and (rec[~h] == -1).all()
+    assert (node[h] >= 0).all() and (rec[h] >= 0).all()
+    assert np.array_equal(rec_tri[rec[h]], tri[h]), "leaf record does not hold the reported triangle"
+    inside = (is_leaf[node[h]] & (first[node[h]] <= rec[h][:, None]) & (rec[h][:, None] < last[node[h]])).any(1)
+    assert inside.all(), f"{(~inside).sum()} hits reported a node that has no leaf with their record"
+
+
+VIEWS = [("pose", 0), ("pose", 49), ("pose", 98), ("at", (300.0, 120.0, 160.0)), ("at", (-1400.0, 30.0, 12.0)),
+         ("at", (200.0, 100.0, 10.0))]
+
+
+@pytest.mark.parametrize("kind,arg", VIEWS)
+def test_primary_kernel_first_hits_and_leaf_vs_oracle(dsrt, poses, mesh10k, oracle_scene10k, kind, arg):
+    """k_tile_entries + k_primary (tile entries on, culling on in Philox mode) against the oracle's
+    first hits under the same jitter: far pose, middle, closest pose, a view from inside the scene
+    box's slab, a grazing view with box corners behind the camera, and a close one."""
+    w, h, spp = 200, 113, 8
+    with dsrt.Context(0) as c:
+        c.upload_scene(*mesh10k)
+        leaf = leaf_tables(*c.download_bvh())
+        if kind == "pose":
+            cam_pos, _, _ = dsrt.pose_to_model_frame(poses[arg])
+        else:
+            cam_pos = np.array(arg, np.float32)
+        cam = dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, DEPTH)
+        for mode, omode, samples in ((dsrt.RNG_PHILOX, 0, (0, 5)), (dsrt.RNG_REF_LCG, 1, (0,))):
+            for s in samples:
+                ours = c.primary_hits(cam, dsrt.make_params(w, h, spp, DEPTH, mode), sample=s)
+                ref = oracle_scene10k.primary_hits(cam12_of(cam), w, h, spp, sample=s, rng_mode=omode)
+                assert_primary_hits(ours, ref, leaf, 300)
+
+
+@pytest.fixture(scope="module")
+def mesh1m(dsrt):
+    return dsrt.synth_mesh(1000000)
+
+
+def test_config2_size_first_hits_of_the_primary_kernel(dsrt, poses, mesh1m):
+    """BASELINE config 2 geometry (1M triangles, 1920x1080, pose 0): the production first-hit stage
+    against the oracle for every pixel, both generators."""
+    tris, mats = mesh1m
+    w, h, spp = 1920, 1080, 64
+    cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[0])
+    cam = dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, DEPTH)
+    sc = oracle.Scene(tris, mats)
+    with dsrt.Context(0) as c:
+        c.upload_scene(tris, mats)
+        leaf = leaf_tables(*c.download_bvh())
+        for mode, omode, s in ((dsrt.RNG_PHILOX, 0, 17), (dsrt.RNG_REF_LCG, 1, 0)):
+            ours = c.primary_hits(cam, dsrt.make_params(w, h, spp, DEPTH, mode), sample=s)
+            ref = sc.primary_hits(cam12_of(cam), w, h, spp, sample=s, rng_mode=omode)
+            assert_primary_hits(ours, ref, leaf, 150000)
+
+
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libref_gpu.so not present")
+def test_config2_size_lcg_frame_identical_to_reference_kernel(dsrt, poses, mesh1m):
+    """1M triangles, 1920x1080, depth 10, 2 spp through the LCG replay: every byte equals the
+    unmodified reference kernel's frame.  The Philox frame of the same configuration then has to
+    agree with it where no randomness is involved: pixels that see no geometry (the first-hit mask,
+    grown by one pixel for the sub-pixel jitter) are black in both, and the lit fraction inside
+    agrees within 2 % (two samples per pixel of two different streams)."""
+    tris, mats = mesh1m
+    w, h, spp = 1920, 1080, 2
+    cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[0])
+    cam = dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, DEPTH)
+    ref = refgpu.RefScene(tris, mats, cam_pos, sun, w, h, spp, DEPTH)
+    rimg, _ = ref.render()
+    ref.close()
+    with dsrt.Context(0) as c:
+        c.upload_scene(tris, mats)
+        c.render(cam, sun, dsrt.make_params(w, h, spp, DEPTH, dsrt.RNG_REF_LCG))
+        img = c.readback_rgb8(spp, 2.0)
+        assert np.array_equal(img, rimg), f"{(img != rimg).any(2).sum()} of {w * h} pixels differ"
+        fs = c.render(cam, sun, dsrt.make_params(w, h, spp, DEPTH, dsrt.RNG_PHILOX))
+        pimg = c.readback_rgb8(spp, 2.0)
+        assert fs.primary_rays == w * h * spp and fs.culled_primary_rays > 0
+        cover = (c.first_hits(cam, w, h, 0.5, 0.5)[0] >= 0).reshape(h, w)[::-1]       # top row first, like the frames
+    grown = cover.copy()
+    grown[1:] |= cover[:-1]; grown[:-1] |= cover[1:]; grown[:, 1:] |= cover[:, :-1]; grown[:, :-1] |= cover[:, 1:]
+    lit_p, lit_l = pimg.any(2), img.any(2)
+    assert not lit_p[~grown].any() and not lit_l[~grown].any()
+    assert abs(lit_p[grown].mean() - lit_l[grown].mean()) <= 0.02, (lit_p[grown].mean(), lit_l[grown].mean())
+
+
+# ---- the legacy boundary with geometry -------------------------------------------------------
+def write_obj(path, tris, mats):
+    """The triangles as an OBJ/MTL the reference's loader maps back to the same material classes
+    (inc/triangle_mesh.h:75-112): %.9g round-trips float32 exactly."""
+    mtl = path.with_suffix(".mtl")
+    with open(mtl, "w") as f:
+        for i, m in enumerate(mats):
+            f.write(f"newmtl m{i}\n")
+            a = m["albedo"]
+            if m["type"] == 1:        # metal: length(Ks) > 0.05, fuzz = 100 / (Ns + 100)
+                f.write(f"Kd 0 0 0\nKs {a['x']:.9g} {a['y']:.9g} {a['z']:.9g}\nNs {100.0 / max(float(m['fuzz']), 1e-3) - 100.0:.9g}\n")
+            elif m["type"] == 2:      # dielectric: d < 0.999
+                f.write(f"Kd 1 1 1\nd 0.5\nNi {float(m['ref_idx']):.9g}\n")
+            else:
+                f.write(f"Kd {a['x']:.9g} {a['y']:.9g} {a['z']:.9g}\n")
+    with open(path, "w") as f:
+        f.write(f"mtllib {mtl.name}\n")
+        for t in tris:
+            for k in ("v0", "v1", "v2"):
+                f.write(f"v {t[k]['x']:.9g} {t[k]['y']:.9g} {t[k]['z']:.9g}\n")
+        cur = -1
+        for i, t in enumerate(tris):
+            if t["material_id"] != cur:
+                cur = int(t["material_id"])
+                f.write(f"usemtl m{cur}\n")
+            f.write(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n")
+
+
+def run_reference_main(binary, workdir, obj_files, pose_line, env_extra):
+    """Lays out <workdir>/iss_model/ISS_stationary.obj and runs the reference's main() from
+    <workdir>/a/b, where its hard-coded ../../iss_model path resolves (src/main.cpp:238)."""
+    model = workdir / "iss_model"
+    model.mkdir(parents=True)
+    for src, name in obj_files:
+        (model / name).write_bytes(Path(src).read_bytes())
+    cwd = workdir / "a" / "b"
+    cwd.mkdir(parents=True)
+    (cwd / "pose.txt").write_text("# cam xyz, model xyz, yaw pitch roll\n" + pose_line + "\n")
+    env = dict(os.environ, **env_extra)
+    p = subprocess.run([str(binary), "--input_txt", "pose.txt", "--output_dir", "out"], cwd=cwd, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    ppm = cwd / "out" / "frame_0000.ppm"
+    assert ppm.exists(), p.stdout[-2000:] + p.stderr[-2000:]
+    raw = ppm.read_bytes()
+    assert raw.startswith(b"P6\n800 450\n255\n")                     # gpu_render.cu:1100-1107
+    return np.frombuffer(raw[len(b"P6\n800 450\n255\n"):], np.uint8).reshape(450, 800, 3)
+
+
+POSE = "5001.5 -2997.5 8009.0  5000.0 -3000.0 8000.0  20.0 0.0 0.0"      # camera 9.5 m from the model, yaw 20 deg
+
+
+@pytest.mark.skipif(not (refgpu.available() and (REF_DIR / "ray_tracer_dropin").exists()), reason="oracle/_ref not built")
+@pytest.mark.parametrize("binary,scene", [("ray_tracer_dropin", "station"), ("ray_tracer_dropin", "synth"),
+                                          ("ray_tracer_binding", "synth")])
+def test_legacy_boundary_renders_geometry_like_the_reference_kernel(dsrt, tmp_path, binary, scene):
+    """The reference's unmodified main.cpp (800x450, 1000 spp, depth 50, its own OBJ loader and, for
+    the drop-in, its own build_gpu_scene) with gpu_render_scene served by libdsrt.so, LCG replay:
+    frame_0000.ppm equals the reference kernel's frame byte for byte.  `station` is the textured
+    fixture with every material class; `synth` a 3000-triangle station written out as an OBJ (the
+    binding example forwards no textures, so it only gets the untextured one)."""
+    if scene == "station":
+        files = [(OBJ_DIR / n, "ISS_stationary.obj" if n == "station.obj" else n) for n in ("station.obj", "station.mtl", "hull.ppm", "panel.png")]
+        pose = POSE
+    else:
+        tris, mats = dsrt.synth_mesh(3000)
+        src = tmp_path / "src"
+        src.mkdir()
+        write_obj(src / "ISS_stationary.obj", tris, mats)
+        files = [(src / "ISS_stationary.obj", "ISS_stationary.obj"), (src / "ISS_stationary.mtl", "ISS_stationary.mtl")]
+        pose = "5300.0 -2800.0 9600.0  5000.0 -3000.0 8000.0  20.0 0.0 0.0"
+    img = run_reference_main(REF_DIR / binary, tmp_path / "run", files, pose, {"DSRT_RNG": "lcg"})
+    p9 = np.array([float(x) for x in pose.split()])
+    cam_pos, sun, sep = dsrt.pose_to_model_frame(p9)
+    ref = refgpu.RefScene(None, None, cam_pos, sun, 800, 450, 1000, 50, obj=tmp_path / "run" / "iss_model" / "ISS_stationary.obj")
+    rimg, _ = ref.render()
+    ref.close()
+    assert rimg.any(), "the reference frame is black: the test scene is not in view"
+    assert np.array_equal(img, rimg), f"{(img != rimg).any(2).sum()} of 360000 pixels differ"
+
+
+# ---- asynchronous frames ----------------------------------------------------------------------
+def test_async_frames_on_two_slots_equal_the_synchronous_call(dsrt, poses, mesh10k):
+    """Frames k and k+1 in flight together on two slots (own streams, own work memory), read back
+    through the asynchronous tone map + copy: the same bytes and ray counts as dsrt_render_frame."""
+    w, h, spp = 320, 180, 16
+    params = dsrt.make_params(w, h, spp, 50)
+    frames = [0, 30, 60, 90, 98]
+    sync_img, sync_rays = [], []
+    with dsrt.Context(0) as c:
+        c.upload_scene(*mesh10k)
+        for fr in frames:
+            cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[fr])
+            fs = c.render(dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, 50), sun, params)
+            sync_img.append(c.readback_rgb8(spp, 2.0).copy())
+            sync_rays.append(fs.rays)
+        out = [np.empty((h, w, 3), np.uint8) for _ in frames]
+        stats = [None] * len(frames)
+        for k, fr in enumerate(frames):
+            slot = k & 1
+            if k >= 2:
+                stats[k - 2] = c.frame_wait(slot)
+            cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[fr])
+            c.render_async(slot, dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, 50), sun, params)
+            c.readback_rgb8_async(slot, spp, 2.0, out[k])
+        for k in range(max(0, len(frames) - 2), len(frames)):
+            stats[k] = c.frame_wait(k & 1)
+        with pytest.raises(dsrt.DsrtError):
+            c.render_async(0, dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, 50), sun, params)
+            c.render_async(0, dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, 50), sun, params)      # slot busy
+        c.frame_wait(0)
+    for k in range(len(frames)):
+        assert np.array_equal(out[k], sync_img[k]), f"frame {frames[k]}"
+        assert stats[k].rays == sync_rays[k] and stats[k].device_ms > 0
+
+
+def test_deep_paths_past_the_wavefront_depth(dsrt, poses, mesh10k, oracle_scene10k):
+    """Depth 50 (the reference's default): bounces beyond the wavefront depth are finished by the closing
+    k_tail.  The LCG replay must still be the oracle's frame, and a wavefront depth of 2 (every path
+    longer than two bounces goes through the grid-striding tail) must give the same accumulation."""
+    w, h, spp = 96, 54, 4
+    cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[98])
+    cam = dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, 50)
+    with dsrt.Context(0) as c:
+        c.upload_scene(*mesh10k)
+        c.render(cam, sun, dsrt.make_params(w, h, spp, 50, dsrt.RNG_REF_LCG))
+        img = c.readback_rgb8(spp, 2.0)
+        _, orgb, _ = oracle_scene10k.render(cam12_of(cam), w, h, spp, 50, sun, rng_mode=1)
+        assert (img == orgb).all(2).mean() >= 0.995
+        fs = c.render(cam, sun, dsrt.make_params(w, h, spp, 50, dsrt.RNG_PHILOX))
+        acc = c.readback_accum()
+    os.environ["DSRT_WAVE_DEPTH"] = "2"
+    os.environ["DSRT_TAIL_THRESHOLD"] = "64"
+    try:
+        with dsrt.Context(0) as c:
+            c.upload_scene(*mesh10k)
+            fs2 = c.render(cam, sun, dsrt.make_params(w, h, spp, 50, dsrt.RNG_PHILOX))
+            acc2 = c.readback_accum()
+    finally:
+        del os.environ["DSRT_WAVE_DEPTH"], os.environ["DSRT_TAIL_THRESHOLD"]
+    assert np.array_equal(acc, acc2) and fs.rays == fs2.rays
+
+
+# ---- two GPUs ---------------------------------------------------------------------------------
+def read_ppm(path, w, h):
+    return np.fromfile(path, np.uint8)[-w * h * 3:].reshape(h, w, 3)
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs two GPUs")
+def test_two_gpus_frame_parallel_and_sample_sharded_identity(tmp_path):
+    """The CLI on two GPUs against one: frame-parallel frames are the same files; the sample-sharded
+    frame (each GPU renders half of the global sample indices, one ncclReduce of the float
+    accumulation buffer) is identical in RGB8, and its accumulation buffer is allclose 1e-5."""
+    w, h = 400, 225
+    common = ["--input_txt", str(ROOT / "tests" / "golden" / "rendezvous_1s_dt0_01s.txt"), "--width", str(w), "--height", str(h),
+              "--spp", "32", "--max_depth", "10", "--synthetic_tris", "100000", "--frames", "92:98", "--no_png"]
+    runs = {"one": ["--gpus", "1"], "frame": ["--gpus", "2"], "sample": ["--gpus", "2", "--shard", "sample"]}
+    log = []
+    for name, extra in runs.items():
+        p = subprocess.run([str(CLI), *common, "--output_dir", str(tmp_path / name), "--dump_accum", *extra],
+                           capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    for f in sorted((tmp_path / "one").glob("*.ppm")):
+        a = read_ppm(f, w, h)
+        assert np.array_equal(a, read_ppm(tmp_path / "frame" / f.name, w, h)), f"frame-parallel {f.name}"
+        assert np.array_equal(a, read_ppm(tmp_path / "sample" / f.name, w, h)), f"sample-sharded {f.name}"
+        acc1 = np.fromfile(f.with_suffix(".accum"), np.float32)
+        acc2 = np.fromfile((tmp_path / "sample" / f.name).with_suffix(".accum"), np.float32)
+        assert acc1.size == w * h * 3 and np.allclose(acc1, acc2, atol=1e-5), f"accumulation {f.name}"
+        log.append(f"{f.name}: frame-parallel identical, sample-sharded RGB8 identical, max |accum diff| {np.abs(acc1 - acc2).max():.3g}")
+    assert len(log) == 6
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "two_gpu_identity.log").write_text("\n".join(log) + "\n")
