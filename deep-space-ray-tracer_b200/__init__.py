@@ -103,7 +103,7 @@ SYMBOLS = [
     "dsrt_read_pose_file", "dsrt_pose_to_model_frame", "dsrt_camera_look_at_origin",
     "dsrt_synth_mesh", "dsrt_mesh_load_obj", "dsrt_mesh_view", "dsrt_mesh_free",
     "dsrt_write_ppm", "dsrt_write_png", "dsrt_version",
-    "gpu_render_scene",
+    "gpu_render_scene", "dsrt_scene_upload_legacy",
 ]
 
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
@@ -116,6 +116,7 @@ lib.dsrt_stream.argtypes = [_vp]
 lib.dsrt_stream.restype = _vp
 lib.dsrt_scene_upload.argtypes = [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i]
 lib.dsrt_scene_upload_device.argtypes = [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i]
+lib.dsrt_scene_upload_legacy.argtypes = [_vp, _vp, _i, C.POINTER(_i)]
 lib.dsrt_scene_stats.argtypes = [_vp, C.POINTER(SceneStats)]
 lib.dsrt_scene_download.argtypes = [_vp, _vp, C.c_size_t, _vp, C.c_size_t]
 lib.dsrt_render_frame.argtypes = [_vp, C.POINTER(Camera), C.POINTER(_f), C.POINTER(_f), _i,
@@ -313,6 +314,13 @@ class Context:
         self._ck(lib.dsrt_scene_upload_device(self._h, tris_ptr, ntris, mats_ptr, nmats, spheres_ptr or None, nspheres,
                                               None, 0, None, 0))
         return self.scene_stats()
+
+    def upload_scene_legacy(self, legacy_scene_ptr: int, reference_flat_boxes: bool = False):
+        """From a reference GPUScene (host struct of device pointers, include/dsrt_legacy.h); returns
+        (SceneStats, number of triangles masked because the reference's own BVH hides them)."""
+        n = _i(0)
+        self._ck(lib.dsrt_scene_upload_legacy(self._h, legacy_scene_ptr, int(reference_flat_boxes), C.byref(n)))
+        return self.scene_stats(), n.value
 
     def scene_stats(self) -> SceneStats:
         st = SceneStats()

@@ -5,6 +5,7 @@
 // path state, accumulation buffer) and orchestrates the wavefront launches of render.cu.
 // There is deliberately no CPU code path here: every entry that computes needs the device.
 #include "dsrt.h"
+#include "dsrt_legacy.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -294,6 +295,29 @@ __global__ void k_check_material_ids(const DsrtTriangle* __restrict__ tris, int 
     if (i < n && (tris[i].material_id < 0 || tris[i].material_id >= nmats)) atomicAdd(bad, 1u);
 }
 
+// The reference's bbox_hit rejects a box when t_max <= t_min after any axis (gpu_render.cu:312), so a node whose box
+// has zero thickness along an axis is never entered: the triangles of such a LEAF of the reference's own BVH
+// (axis-aligned coplanar panels that its median split happened to group together) are invisible in the reference,
+// for every ray.  Given that BVH (40-byte GPUBVHNode: min[3], max[3], left, right, tri_offset, tri_count; leaf when
+// tri_count > 0), this collapses those triangles to a point in OUR copy of the triangle array, so that they can never
+// be hit here either.  One thread per reference node.
+__global__ void k_mask_flat_leaves(const float* __restrict__ ref_nodes, int num_nodes, const int* __restrict__ tri_indices,
+                                   DsrtTriangle* tris, int ntris, uint32_t* masked) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_nodes) return;
+    const float* nd = ref_nodes + (size_t)i * 10;
+    const int off = __float_as_int(nd[8]), cnt = __float_as_int(nd[9]);
+    if (cnt <= 0) return;
+    if (!(nd[0] == nd[3] || nd[1] == nd[4] || nd[2] == nd[5])) return;
+    for (int k = 0; k < cnt; ++k) {
+        const int t = tri_indices[off + k];
+        if (t < 0 || t >= ntris) continue;
+        tris[t].v1 = tris[t].v0;
+        tris[t].v2 = tris[t].v0;
+        atomicAdd(masked, 1u);
+    }
+}
+
 // Common tail of the two upload entry points.  `tris`/`mats`/`textures`/`pool` are host
 // pointers when from_device is false and device pointers (on ctx's GPU) when it is true.
 int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris, int ntris,
@@ -303,6 +327,8 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
     if (ntris < 0 || nmats < 0 || (ntris > 0 && !tris) || (nmats > 0 && !mats))
         return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad triangle/material arguments");
     if ((ntris > 0 || nspheres > 0) && nmats == 0) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: geometry without materials");
+    if (ntris >= (1 << kPoolIndexBits))
+        return fail(ctx, DSRT_EUNSUPPORTED, "at most %d triangles (record positions are packed into %u bits, csrc/bvh8.cuh)", (1 << kPoolIndexBits) - 1, kPoolIndexBits);
     if (nspheres < 0 || (nspheres > 0 && !spheres)) return fail(ctx, DSRT_EINVAL, "dsrt_scene_upload: bad sphere arguments");
     // Spheres are few and are packed on the host (with the material table at hand, for the emissive ones): arrays that
     // live on the device come back first.
@@ -439,6 +465,39 @@ extern "C" int dsrt_scene_upload_device(dsrt_ctx* ctx, const DsrtTriangle* tris_
     if (!ctx) return DSRT_EINVAL;
     return scene_upload_impl(ctx, true, tris_device, ntris, mats_device, nmats, spheres_device, nspheres,
                              textures_device, ntextures, texture_pool_device, texture_pool_floats);
+}
+
+extern "C" int dsrt_scene_upload_legacy(dsrt_ctx* ctx, const DsrtLegacyScene* scene, int reference_flat_boxes, int* masked_triangles) {
+    if (!ctx || !scene) return DSRT_EINVAL;
+    if (masked_triangles) *masked_triangles = 0;
+    const DsrtTriangle* tris = scene->triangles;
+    DsrtTriangle* copy = nullptr;
+    if (reference_flat_boxes && scene->num_triangles > 0 && scene->bvh_nodes && scene->num_bvh_nodes > 0 && scene->tri_indices) {
+        CK(cudaSetDevice(ctx->device));
+        const int rc0 = sync_all_slots(ctx);
+        if (rc0) return rc0;
+        const size_t bytes = sizeof(DsrtTriangle) * (size_t)scene->num_triangles;
+        CK(cudaMalloc(&copy, bytes));
+        uint32_t* counter = ctx->slots[0].counters + C_COUNT + 2;
+        cudaError_t e = cudaMemcpyAsync(copy, scene->triangles, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), ctx->stream);
+        if (e == cudaSuccess) {
+            k_mask_flat_leaves<<<(scene->num_bvh_nodes + 127) / 128, 128, 0, ctx->stream>>>(
+                (const float*)scene->bvh_nodes, scene->num_bvh_nodes, scene->tri_indices, copy, scene->num_triangles, counter);
+            e = cudaGetLastError();
+        }
+        uint32_t n = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&n, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(copy); return fail(ctx, DSRT_ECUDA, "flat-leaf masking: %s", cudaGetErrorString(e)); }
+        if (masked_triangles) *masked_triangles = (int)n;
+        tris = copy;
+    }
+    const int rc = scene_upload_impl(ctx, true, tris, scene->num_triangles, scene->materials, scene->num_materials,
+                                     scene->spheres, scene->num_spheres, scene->textures, scene->num_textures,
+                                     scene->texture_pool, scene->texture_pool_floats);
+    if (copy) cudaFree(copy);
+    return rc;
 }
 
 extern "C" int dsrt_scene_stats(dsrt_ctx* ctx, DsrtSceneStats* out) {

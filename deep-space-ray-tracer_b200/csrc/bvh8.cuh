@@ -57,6 +57,9 @@ constexpr int kMaxLeafTris = 3;
 #endif
 constexpr int kSmemStack = DSRT_SMEM_STACK;          // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 40;        // overflow entries per thread in local memory
+#ifndef DSRT_PREFETCH_NEXT
+#define DSRT_PREFETCH_NEXT 0           // 1: visit() prefetches the node of the next visit into L1 (see there)
+#endif
 
 struct TravRay {
     float ox, oy, oz, tmin;
@@ -78,6 +81,13 @@ __device__ __forceinline__ float safe_rcp_dir(float d) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r;
+}
+
+// What init() derives from a direction: {1/dx, 1/dy, 1/dz (safe_rcp_dir), bits(7 - octant)}.
+__device__ __forceinline__ float4 prepare_dir(float dx, float dy, float dz) {
+    const float ix = safe_rcp_dir(dx), iy = safe_rcp_dir(dy), iz = safe_rcp_dir(dz);
+    const uint32_t oct = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+    return make_float4(ix, iy, iz, __uint_as_float(7u - oct));
 }
 
 // Per-thread traversal stack: the first kSmemStack entries live in shared memory laid out
@@ -285,6 +295,23 @@ struct LaneTravT {
         stack.sp = 0;
     }
 
+    // init() for a ray whose inverse direction and octant were prepared beforehand (prepare_dir) -- by a whole warp
+    // for the rays it has staged, instead of by the few lanes that happen to take a new ray in a given iteration.
+    __device__ __forceinline__ void init_prepared(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_, float4 inv,
+                                                  float tmin_, float tmax_, bool any_hit_, TravStack& stack) {
+        ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_;
+        idx = inv.x; idy = inv.y; idz = inv.z;
+        tmin = tmin_; tmax = tmax_;
+        hu = 0.f; hv = 0.f; htri = -1;
+        if (TRACK) hnode = 0xFFFFFFFFu;
+        octinv = __float_as_uint(inv.w);
+        ngroup = make_uint2(0u, 0x80000000u);
+        any_hit = any_hit_;
+        stack.sp = 0;
+    }
+
+    __device__ __forceinline__ void set_hnode(uint32_t node) { if (TRACK) hnode = node; }
+
     __device__ __forceinline__ bool step(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
                                          TravStack& stack) {
         uint2 tgroup;
@@ -321,6 +348,70 @@ struct LaneTravT {
                 if (any_hit) return true;
             }
         }
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (stack.sp == 0) return true;
+            ngroup = stack.pop();
+        }
+        return false;
+    }
+
+    // ---- step() in three parts, for the trace loops that test triangles warp-cooperatively (pooled_tri_test) ----
+    // visit(): the node half of step().  Returns the triangles this visit exposed {first record, 24-bit mask}.
+    __device__ __forceinline__ uint2 visit(const uint4* __restrict__ nodes, TravStack& stack, uint32_t& cur_node) {
+        uint2 tgroup;
+        cur_node = 0u;
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t bit = 31u - __clz(ngroup.y);
+            ngroup.y &= ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ octinv;
+            const uint32_t rel = __popc(ngroup.y & 0xFFu & ((1u << slot) - 1u));
+            const uint32_t node_index = ngroup.x + rel;
+            cur_node = node_index;
+            if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
+            uint32_t child_base, tri_base, imask, tri_hits;
+            const uint32_t slots = node_test(nodes, node_index, ox, oy, oz, idx, idy, idz, tmin, tmax,
+                                             one, child_base, tri_base, imask, tri_hits);
+            ngroup = make_uint2(child_base, ((uint32_t)perm[(octinv << 8) + slots] << 24) | imask);
+            tgroup = make_uint2(tri_base, tri_hits);
+#if DSRT_PREFETCH_NEXT
+            // the node the next visit will fetch is known now: start its two cache lines on their way while the
+            // triangles of this visit are tested
+            if (ngroup.y > 0x00FFFFFFu) {
+                const uint32_t nbit = 31u - __clz(ngroup.y);
+                const uint32_t nslot = (nbit - 24u) ^ octinv;
+                const uint32_t nrel = __popc(imask & ((1u << nslot) - 1u));
+                const char* np = reinterpret_cast<const char*>(nodes + (size_t)(child_base + nrel) * kNodeWords);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 80));
+            }
+#endif
+        } else {
+            tgroup = ngroup;
+            ngroup = make_uint2(0u, 0u);
+        }
+        return tgroup;
+    }
+    // The sequential triangle loop of step() on its own; true when an any-hit ray found its occluder.
+    __device__ __forceinline__ bool test_own(const float4* __restrict__ tris, uint2 tgroup, uint32_t cur_node) {
+        const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
+        while (tgroup.y != 0u) {
+            const uint32_t bit = 31u - __clz(tgroup.y);
+            tgroup.y &= ~(1u << bit);
+            const uint32_t ti = tgroup.x + bit;
+            float4 ra, rb, rc;
+            load_tri_record(tris + (size_t)ti * kTriWords, ra, rb, rc);
+            float t, u, v;
+            if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
+                tmax = t; hu = u; hv = v; htri = (int)ti;
+                if (TRACK) hnode = cur_node;
+                if (any_hit) return true;
+            }
+        }
+        return false;
+    }
+    // settle(): the end of step(): true when the ray is finished.
+    __device__ __forceinline__ bool settle(TravStack& stack, bool occluded) {
+        if (occluded) return true;
         if (ngroup.y <= 0x00FFFFFFu) {
             if (stack.sp == 0) return true;
             ngroup = stack.pop();
@@ -368,5 +459,97 @@ struct LaneTravT {
     }
 };
 using LaneTrav = LaneTravT<false>;
+
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative triangle test.
+//
+// A node visit exposes 0.3 triangles per ray on average, so the per-lane triangle loop of step() runs at 3-5
+// of 32 lanes for as many rounds as the busiest lane has triangles (profiles/r02_b: 30 % of the traversal
+// kernels' instructions at 3.6 threads per instruction in k_trace, 5 in k_primary).  Here the triangles that
+// the lanes of a warp exposed in one step are pooled in shared memory (an exclusive scan of the per-lane
+// counts gives every owner its place), each lane then tests ONE triangle of the pool -- fetching the owner's
+// ray with shuffles -- and writes {t, u, v, accepted} back; finally every owner folds its own results in the
+// order the sequential loop would have tested them, with the same acceptance rule (not t > t_max of the
+// moment), so the outcome is the sequential loop's bit for bit, equal-t ties included.
+// ---------------------------------------------------------------------------------------
+constexpr int kPoolCap = 32;             // triangles tested per round: one per lane
+constexpr uint32_t kPoolIndexBits = 27;  // record positions below 2^27 (checked at upload); the owner lane sits above
+struct TriPool {                         // one per warp
+    uint32_t entry[kPoolCap];            // owner lane << 27 | record position
+    float4 result[kPoolCap];             // t, u, v, accepted (1.0f / 0.0f)
+};
+#ifndef DSRT_POOL_MIN_COUNT
+#define DSRT_POOL_MIN_COUNT 99           // pool only when some lane holds at least this many triangles; above 24 = never.
+#endif                                   // MEASURED ON B200 AND SWITCHED OFF (profiles/r02_ab_variants.txt): C2 traversal 9.17 ms
+                                         // with the per-lane loop, 9.67 ms pooled (threshold 2), 9.52 (3), 9.68 (always), all at 7
+                                         // blocks per SM (the pooled loop needs 72 registers; at 64 it spills and takes 10.6 ms).
+                                         // The scan, seven shuffles, two shared-memory round trips and three warp barriers per step
+                                         // cost more than the 2.5 sequential rounds at ~4 lanes that they replace.
+
+// Called by all 32 lanes in converged code; `tg` is what visit() returned (ignored for lanes without a ray).
+// Returns true for an any-hit ray that found its occluder.
+template <class Trav>
+__device__ __forceinline__ bool pooled_tri_test(Trav& L, bool active, uint2 tg, uint32_t cur_node,
+                                                const float4* __restrict__ tris, TriPool* pool, uint32_t lane) {
+    uint32_t bits = active ? tg.y : 0u;
+#if DSRT_POOL_MIN_COUNT > 24
+    if (bits != 0u) return L.test_own(tris, make_uint2(tg.x, bits), cur_node);      // never pool (A/B builds)
+    return false;
+#endif
+    if (__ballot_sync(0xffffffffu, __popc(bits) >= DSRT_POOL_MIN_COUNT) == 0u) {
+        if (bits != 0u) return L.test_own(tris, make_uint2(tg.x, bits), cur_node);
+        return false;
+    }
+    bool occluded = false;
+    const uint32_t index_mask = (1u << kPoolIndexBits) - 1u;
+    while (true) {
+        const uint32_t cnt = __popc(bits);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += n;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0u) break;
+        const uint32_t excl = incl - cnt;
+        // owners list their triangles in the order the sequential loop tests them (highest bit first)
+        uint32_t my_n = 0u;
+        while (bits != 0u && excl + my_n < (uint32_t)kPoolCap) {
+            const uint32_t bit = 31u - __clz(bits);
+            bits &= ~(1u << bit);
+            pool->entry[excl + my_n] = (lane << kPoolIndexBits) | (tg.x + bit);
+            ++my_n;
+        }
+        __syncwarp();
+        const uint32_t n_pool = min(total, (uint32_t)kPoolCap);
+        const bool has = lane < n_pool;
+        const uint32_t e = has ? pool->entry[lane] : 0u;
+        const uint32_t owner = e >> kPoolIndexBits;
+        const V3 orig = v3(__shfl_sync(0xffffffffu, L.ox, owner), __shfl_sync(0xffffffffu, L.oy, owner), __shfl_sync(0xffffffffu, L.oz, owner));
+        const V3 dir = v3(__shfl_sync(0xffffffffu, L.dx, owner), __shfl_sync(0xffffffffu, L.dy, owner), __shfl_sync(0xffffffffu, L.dz, owner));
+        const float tmin = __shfl_sync(0xffffffffu, L.tmin, owner);
+        if (has) {
+            float4 ra, rb, rc;
+            load_tri_record(tris + (size_t)(e & index_mask) * kTriWords, ra, rb, rc);
+            float t = 0.f, u = 0.f, v = 0.f;
+            // the upper end of the interval is the owner's business (its t_max shrinks as it folds the results)
+            const bool ok = tri_test(ra, rb, rc, orig, dir, tmin, __int_as_float(0x7f800000), t, u, v);
+            pool->result[lane] = make_float4(t, u, v, ok ? 1.0f : 0.0f);
+        }
+        __syncwarp();
+        for (uint32_t k = 0; k < my_n; ++k) {
+            const float4 r = pool->result[excl + k];
+            if (r.w != 0.0f && !(r.x > L.tmax)) {
+                L.tmax = r.x; L.hu = r.y; L.hv = r.z;
+                L.htri = (int)(pool->entry[excl + k] & index_mask);
+                L.set_hnode(cur_node);
+                if (L.any_hit) { occluded = true; bits = 0u; break; }
+            }
+        }
+        __syncwarp();                     // the pool is rewritten by the next round
+    }
+    return occluded;
+}
 
 }  // namespace dsrt

@@ -7,6 +7,7 @@
 //
 // Environment: DSRT_RNG=lcg selects the bit-compatible replay of the reference's per-pixel
 // LCG; default is the counter-based Philox stream.  DSRT_DEVICE picks the GPU.
+// DSRT_REF_FLATBOX=1 reproduces the reference's invisible zero-thickness leaves (dsrt_legacy.h).
 #include "dsrt.h"
 #include "dsrt_legacy.h"
 
@@ -51,10 +52,12 @@ extern "C" void gpu_render_scene(const DsrtLegacyScene* scene, int width, int he
     dsrt_ctx* ctx = shim_ctx();
     if (!ctx) return;
 
-    int rc = dsrt_scene_upload_device(ctx, scene->triangles, scene->num_triangles,
-                                      scene->materials, scene->num_materials, scene->spheres, scene->num_spheres,
-                                      scene->textures, scene->num_textures,
-                                      scene->texture_pool, scene->texture_pool_floats);
+    // DSRT_REF_FLATBOX=1: triangles the reference cannot see because its own BVH put them into a zero-thickness leaf
+    // box stay invisible here too (include/dsrt_legacy.h)
+    const char* flat = std::getenv("DSRT_REF_FLATBOX");
+    int masked = 0;
+    int rc = dsrt_scene_upload_legacy(ctx, scene, (flat && std::atoi(flat) != 0) ? 1 : 0, &masked);
+    if (rc == DSRT_OK && masked > 0) std::fprintf(stderr, "gpu_render_scene: %d triangles in flat reference leaves masked (DSRT_REF_FLATBOX)\n", masked);
     if (rc != DSRT_OK) { std::fprintf(stderr, "gpu_render_scene: %s\n", dsrt_last_error(ctx)); return; }
 
     DsrtRenderParams params = scene->params;

@@ -60,6 +60,17 @@ typedef struct DsrtLegacyScene {
 
 void gpu_render_scene(const DsrtLegacyScene* scene, int width, int height);
 
+/* The scene half of gpu_render_scene on its own: builds the B200 scene from a reference GPUScene (device arrays,
+ * consumed in place; see dsrt_scene_upload_device).  reference_flat_boxes != 0 also reproduces a quirk that depends on
+ * the reference's OWN BVH, which the GPUScene carries (bvh_nodes, tri_indices): its box test rejects zero-thickness
+ * boxes (src/gpu_render.cu:312: `if (t_max <= t_min) return false`), so the triangles of a reference leaf whose box is
+ * flat along an axis -- axis-aligned coplanar panels grouped by its median split, src/gpu_scene_builder.cpp:343-442 --
+ * are invisible in the reference.  With the switch those triangles are made unhittable here too (their number is
+ * returned through masked_triangles, may be NULL); without it this path renders them.  gpu_render_scene turns the
+ * switch on when the environment has DSRT_REF_FLATBOX=1. */
+struct dsrt_ctx;
+int dsrt_scene_upload_legacy(struct dsrt_ctx* ctx, const DsrtLegacyScene* scene, int reference_flat_boxes, int* masked_triangles);
+
 #ifdef __cplusplus
 }
 #endif

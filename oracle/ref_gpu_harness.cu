@@ -178,6 +178,13 @@ int ref_scene_arrays(void* h, int n[6], void* tris, void* mats, void* spheres, v
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// The reference's GPUScene itself (a host struct of device pointers, 384 bytes): what its main() hands to
+// gpu_render_scene -- for tests of the legacy boundary (include/dsrt_legacy.h).
+const void* ref_scene_legacy(void* h) {
+    RefScene* R = (RefScene*)h;
+    return R ? (const void*)&R->scene : nullptr;
+}
+
 int ref_scene_info(void* h, int* num_bvh_nodes, int* normal_mismatches, float* build_ms, float camera12[12]) {
     RefScene* R = (RefScene*)h;
     if (!R) return -1;

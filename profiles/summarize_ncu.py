@@ -2,7 +2,7 @@
 
     python profiles/summarize_ncu.py launches gpurun_out/launches.csv  > profiles/rNN_launches.txt
     python profiles/summarize_ncu.py kernel   gpurun_out/prof.ncu-rep  > profiles/rNN_kernel.txt
-    python profiles/summarize_ncu.py traffic  gpurun_out/traffic.ncu-rep "<workload name>" > profiles/trace_ncu_summary.json
+    python profiles/summarize_ncu.py traffic  gpurun_out/traffic.ncu-rep "<workload name>" [batches per step] > profiles/trace_ncu_summary.json
         (a capture of every k_primary / k_trace / k_tail launch of `bench.py --steps 1 --warmup 1`: DRAM bytes
          of the traversal launches of the LAST step, which bench.py reports as roofline.traffic)
 """
@@ -79,7 +79,8 @@ def kernel(path):
             print(f"{k:88s} {units[i]:16s} " + " | ".join(r[i] for r in data))
 
 
-def traffic(path, workload):
+def traffic(path, workload, batches=1):
+    """batches = k_primary launches per step (a step whose samples do not fit one batch has several)."""
     import json
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -103,7 +104,7 @@ def traffic(path, workload):
             continue
         cur.append({"kernel": short, "dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum"),
                     "l2_to_sm_read_bytes": val(r, "l1tex__m_xbar2l1tex_read_bytes.sum"), "ms": val(r, "gpu__time_duration.sum")})
-    last = steps[-1]
+    last = [x for st in steps[-batches:] for x in st]
     res = {"workload": workload, "source": path.split("/")[-1],
            "note": "ncu --set full, default cache control (every launch starts with cold caches): an upper bound on the "
                    "DRAM traffic of the same launches inside an un-profiled step",
@@ -119,6 +120,6 @@ def traffic(path, workload):
 
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
-        traffic(sys.argv[2], sys.argv[3])
+        traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     else:
         {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])

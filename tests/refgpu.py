@@ -35,6 +35,8 @@ def lib():
         _lib.ref_render.argtypes = [vp, vp, C.POINTER(f)]
         _lib.ref_first_hits.argtypes = [vp, f, f, vp, vp, vp, vp]
         _lib.ref_trace.argtypes = [vp, vp, i, vp, vp, vp, vp]
+        _lib.ref_scene_legacy.argtypes = [vp]
+        _lib.ref_scene_legacy.restype = vp
         _lib.ref_scene_destroy.argtypes = [vp]
         _lib.ref_scene_destroy.restype = None
     return _lib
@@ -80,6 +82,10 @@ class RefScene:
         assert lib().ref_scene_arrays(self.h, n.ctypes.data, tris.ctypes.data, mats.ctypes.data, sph.ctypes.data,
                                       th.ctypes.data, pool.ctypes.data) == 0
         return {"counts": n, "tris": tris, "mats": mats, "spheres": sph, "textures": th, "pool": pool}
+
+    def legacy_scene_ptr(self) -> int:
+        """Address of the reference's GPUScene (host struct holding device pointers)."""
+        return lib().ref_scene_legacy(self.h)
 
     def set_seed(self, seed: int):
         assert lib().ref_scene_set_seed(self.h, seed) == 0

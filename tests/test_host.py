@@ -150,6 +150,35 @@ def test_product_never_touches_the_oracle():
             assert "liboracle" not in text and "oracle/" not in text and "import oracle" not in text, p
 
 
+def test_bench_touches_the_oracle_only_in_its_baseline_legs():
+    """bench.py may execute oracle/ code (tests/oracle.py, refcpu.py, refgpu.py, synthmesh.py) only in the legs that
+    time the reference: cpu_baseline, ref_gpu_kernel and run_reference (--impl reference).  The timed product path
+    -- run_dsrt and everything it calls -- must not import them, and the reference arm must not import the product."""
+    import ast
+    tree = ast.parse((ROOT / "bench.py").read_text())
+    checker_modules = {"oracle", "refcpu", "refgpu", "synthmesh"}
+    allowed = {"cpu_baseline", "ref_gpu_kernel", "run_reference"}
+    seen = set()
+    for fn in [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))]:
+        for node in ast.walk(fn):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name.split(".")[0] for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module.split(".")[0]]
+            for nm in names:
+                if nm in checker_modules:
+                    assert fn.name in allowed, f"bench.py: {fn.name} imports {nm}"
+                    seen.add(fn.name)
+                if nm in ("dsrt_b200",):
+                    assert fn.name not in ("run_reference", "cpu_baseline", "ref_gpu_kernel"), f"bench.py: {fn.name} maps the product library"
+    for node in tree.body:                      # nothing at module level either
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not (set(m.split(".")[0] for m in mods) & (checker_modules | {"dsrt_b200"})), mods
+    assert seen == allowed
+
+
 def test_box_screen_bounds_are_conservative(dsrt, poses):
     """dsrt_box_screen_bounds (host arithmetic behind k_primary's early miss): every point of the box,
     projected with the reference camera model u = (x + jx) / (W - 1) (gpu_render.cu:952-967), must
