@@ -79,6 +79,7 @@ struct dsrt_ctx {
     Bvh8 bvh;
     float4* d_mats = nullptr;
     int nmats = 0;
+    int mat_classes = 1;               // how many of {lambertian/emitter, metal, dielectric} the material table holds
     DsrtTextureHeader* d_tex = nullptr;
     float* d_pool = nullptr;
     int ntex = 0, pool_floats = 0;
@@ -130,6 +131,7 @@ void free_scene(dsrt_ctx* c) {
     cudaFree(c->d_spheres); c->d_spheres = nullptr;
     cudaFree(c->d_sphere_lights); c->d_sphere_lights = nullptr;
     c->nmats = c->ntex = c->pool_floats = c->nspheres = c->nsphere_lights = 0;
+    c->mat_classes = 1;
     c->have_scene = false;
 }
 
@@ -370,6 +372,21 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
         CK(cudaMalloc(&ctx->d_mats, sizeof(DsrtMaterial) * (size_t)nmats));
         CK(cudaMemcpyAsync(ctx->d_mats, mats, sizeof(DsrtMaterial) * (size_t)nmats, kind, ctx->stream));
         ctx->nmats = nmats;
+        // which material classes occur (k_shade bins its hits by class only when there is more than one)
+        std::vector<DsrtMaterial> tmp;
+        const DsrtMaterial* hm = mats_host;
+        if (from_device && h_mats.empty() && nmats <= kShadeClassTable) {
+            tmp.resize((size_t)nmats);
+            CK(cudaMemcpy(tmp.data(), mats, sizeof(DsrtMaterial) * (size_t)nmats, cudaMemcpyDeviceToHost));
+            hm = tmp.data();
+        }
+        bool seen[3] = {false, false, false};
+        if (!from_device || hm != mats) {
+            for (int i = 0; i < nmats; ++i) seen[hm[i].type == DSRT_MAT_METAL ? 1 : (hm[i].type == DSRT_MAT_DIELECTRIC ? 2 : 0)] = true;
+            ctx->mat_classes = (int)seen[0] + (int)seen[1] + (int)seen[2];
+        } else {
+            ctx->mat_classes = 1;       // table too large to bin anyway
+        }
     }
     if (ntextures > 0) {
         CK(cudaMalloc(&ctx->d_tex, sizeof(DsrtTextureHeader) * (size_t)ntextures));
@@ -550,6 +567,8 @@ void fill_scene_consts(dsrt_ctx* ctx, FrameConst& fc) {
     fc.textures = ctx->d_tex;
     fc.texture_pool = ctx->d_pool;
     fc.num_nodes = ctx->bvh.num_nodes;
+    fc.num_materials = ctx->nmats;
+    fc.shade_bins = ctx->mat_classes > 1 && ctx->nmats <= kShadeClassTable;
     {
         float ext = 0.f;
         for (int k = 0; k < 3; ++k) {

@@ -57,6 +57,11 @@ constexpr int kMaxLeafTris = 3;
 #endif
 constexpr int kSmemStack = DSRT_SMEM_STACK;          // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 40;        // overflow entries per thread in local memory
+#ifndef DSRT_TRI_PER_STEP
+#define DSRT_TRI_PER_STEP 2            // 0: a step drains the triangles its node visit exposed; n > 0: at most n per step (step_bounded).
+                                       // Measured on B200 (profiles/r02_ab_variants.txt), C2 traversal ms: drain 8.71, n = 1: 8.84,
+                                       // n = 2: 8.12, n = 3: 8.58; C5: 46.2 / 45.5 / 43.1 / 45.5
+#endif
 #ifndef DSRT_PREFETCH_NEXT
 #define DSRT_PREFETCH_NEXT 0           // 1: visit() prefetches the node of the next visit into L1 (see there)
 #endif
@@ -275,6 +280,8 @@ struct LaneTravT {
     float hu, hv;
     int htri;                     // position in the leaf-ordered record array, -1 = none, -2 - i = sphere i
     uint32_t hnode;               // TRACK only: the node visited when htri was accepted
+    uint32_t tnode;               // TRACK only: the node whose triangles are pending in tpend
+    uint2 tpend;                  // DSRT_TRI_PER_STEP > 0: triangles of the last node visit that still wait for their test
     uint32_t octinv;
     uint2 ngroup;
     uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
@@ -291,6 +298,7 @@ struct LaneTravT {
         const uint32_t oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
         octinv = 7u - oct;
         ngroup = make_uint2(0u, 0x80000000u);      // the root as a one-bit node group
+        tpend = make_uint2(0u, 0u);
         any_hit = any_hit_;
         stack.sp = 0;
     }
@@ -306,6 +314,7 @@ struct LaneTravT {
         if (TRACK) hnode = 0xFFFFFFFFu;
         octinv = __float_as_uint(inv.w);
         ngroup = make_uint2(0u, 0x80000000u);
+        tpend = make_uint2(0u, 0u);
         any_hit = any_hit_;
         stack.sp = 0;
     }
@@ -353,6 +362,38 @@ struct LaneTravT {
             ngroup = stack.pop();
         }
         return false;
+    }
+
+    // step() with at most DSRT_TRI_PER_STEP triangle tests per call.  A node visit exposes 0.3 triangles per ray on
+    // average but now and then several at once, and in step() the whole warp waits while one lane drains its three:
+    // the triangle loop ran ~2.5 rounds per step at 3.6 of 32 lanes (profiles/r02_b_source_lines.txt).  Here a lane
+    // tests a bounded number per call and KEEPS the rest (tpend); while it has triangles pending it does not visit
+    // another node -- its t_max stays as tight as in step(), it just sits out the node test of the next call -- so
+    // every call costs one node visit and one short round of triangle tests at three times the width.  Hits are
+    // those of step() (the same triangles are tested against the same shrinking interval, in the same order).
+    __device__ __forceinline__ bool step_bounded(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                 TravStack& stack, int max_tests) {
+        if (tpend.y == 0u) {
+            uint32_t cur_node;
+            tpend = visit(nodes, stack, cur_node);
+            if (TRACK) tnode = cur_node;
+        }
+        const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
+        for (int k = 0; k < max_tests && tpend.y != 0u; ++k) {
+            const uint32_t bit = 31u - __clz(tpend.y);
+            tpend.y &= ~(1u << bit);
+            const uint32_t ti = tpend.x + bit;
+            float4 ra, rb, rc;
+            load_tri_record(tris + (size_t)ti * kTriWords, ra, rb, rc);
+            float t, u, v;
+            if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
+                tmax = t; hu = u; hv = v; htri = (int)ti;
+                if (TRACK) hnode = tnode;
+                if (any_hit) return true;
+            }
+        }
+        if (tpend.y != 0u) return false;          // the rest of this node's triangles: next call
+        return settle(stack, false);
     }
 
     // ---- step() in three parts, for the trace loops that test triangles warp-cooperatively (pooled_tri_test) ----

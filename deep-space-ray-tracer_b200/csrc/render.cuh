@@ -37,7 +37,8 @@ struct FrameConst {
     const float* texture_pool;
     const float4* spheres;            // 2 x float4 per sphere: centre.xyz, radius | 1/radius, bits(material), 0, 0
     const int* sphere_lights;         // indices of the emissive spheres, in sphere order (gpu_render.cu:842-848)
-    int num_nodes, num_textures, texture_pool_floats;
+    int num_nodes, num_textures, texture_pool_floats, num_materials;
+    int shade_bins;                   // 1: k_shade collects hits per material class (more than one class in the table, and it fits)
     int num_spheres, num_sphere_lights;
     float scene_lo[3], scene_hi[3];   // scene bounds padded by 2^-16 of the scene size (root-box test)
     // camera (reference GPUCamera fields that the kernel reads)
@@ -84,6 +85,7 @@ struct FrameConst {
 struct LaunchDims {
     int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0, tail_blocks = 0;
 };
+constexpr int kShadeClassTable = 1024;          // k_shade's shared-memory table of material classes
 constexpr uint32_t kTailAll = 0xFFFFFFFFu;      // launch_tail threshold: finish whatever is left
 
 // Host-callable launchers (all asynchronous on `s`).

@@ -106,8 +106,8 @@ def traffic(path, workload, batches=1):
                     "l2_to_sm_read_bytes": val(r, "l1tex__m_xbar2l1tex_read_bytes.sum"), "ms": val(r, "gpu__time_duration.sum")})
     last = [x for st in steps[-batches:] for x in st]
     res = {"workload": workload, "source": path.split("/")[-1],
-           "note": "ncu --set full, default cache control (every launch starts with cold caches): an upper bound on the "
-                   "DRAM traffic of the same launches inside an un-profiled step",
+           "note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, default cache control (every launch starts with "
+                   "cold caches): an upper bound on the DRAM traffic of the same launches inside an un-profiled step",
            "launches_in_step": len(last),
            "dram_bytes_per_step": sum(x["dram_read"] + x["dram_write"] for x in last),
            "dram_read_bytes_per_step": sum(x["dram_read"] for x in last),
@@ -118,8 +118,44 @@ def traffic(path, workload, batches=1):
     print(json.dumps(res, indent=1))
 
 
+def lines(path, kernel_regex, skip="0", top="45"):
+    """Per source line of one launch: share of the executed warp instructions, average active threads per
+    instruction (lane utilisation) and share of the stall samples -- from `ncu --import-source on` reports of code
+    built with -lineinfo.    python profiles/summarize_ncu.py lines <rep> <kernel regex> [launch-skip] [top n]"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name",
+                          f"regex:{kernel_regex}", "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
+    cur, hdr, acc, fn = None, None, {}, ""
+    for r in csv.reader(out.splitlines()):
+        if len(r) >= 2 and r[0] == "File Path":
+            cur, hdr = r[1].split("/")[-1], None
+            continue
+        if r and r[0] == "Function Name":
+            fn = r[1]
+            continue
+        if r and r[0] == "Line No":
+            hdr = r
+            continue
+        if hdr is None or len(r) < 10 or r[2] != "-":       # keep the per-line aggregates, skip the per-SASS rows
+            continue
+        try:
+            ie, te, smp = float(r[7]), float(r[8]), float(r[6])
+        except ValueError:
+            continue
+        o = acc.setdefault((cur, int(r[0])), [0.0, 0.0, 0.0, r[1].strip()[:110]])
+        o[0] += ie; o[1] += te; o[2] += smp
+    tot = sum(o[0] for o in acc.values()) or 1.0
+    tott = sum(o[1] for o in acc.values())
+    tots = sum(o[2] for o in acc.values()) or 1.0
+    print(f"# {fn}: {tot:.4g} warp instructions, {tott / tot:.2f} threads per instruction, {int(tots)} stall samples")
+    print("# file line | % of instructions | threads per instruction | % of samples | source")
+    for (f, l), o in sorted(acc.items(), key=lambda kv: -kv[1][0])[:int(top)]:
+        print(f"{f:14s} {l:5d} {100 * o[0] / tot:6.2f}% {o[1] / max(o[0], 1):5.1f} {100 * o[2] / tots:6.2f}%  {o[3]}")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "traffic":
+    if sys.argv[1] == "lines":
+        lines(*sys.argv[2:6])
+    elif sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     else:
         {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
