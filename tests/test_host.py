@@ -252,3 +252,23 @@ def test_cli_host_side_without_a_gpu(dsrt, tmp_path):
         assert r.returncode != 0
         assert "no usable CUDA device" in r.stderr and "no CPU path" in r.stderr
         assert list(out.iterdir()) == []
+
+
+def test_reference_arm_of_bench_does_not_map_the_product_library(tmp_path):
+    """`bench.py --impl reference` times the reference's CPU classes; mesh, poses and camera come from oracle-side
+    helpers, so libdsrt.so must not even be loaded by that process (the dynamic loader's own file log says so)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LD_DEBUG="files", LD_DEBUG_OUTPUT=str(tmp_path / "ld"))
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--tris", "3000",
+                        "--width", "96", "--height", "54", "--spp", "4", "--depth", "4", "--cpu_step", "2"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-1500:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port")
+    loaded = "".join(f.read_text(errors="ignore") for f in tmp_path.glob("ld*"))
+    assert "liboracle" in loaded or "libref_cpu" in loaded
+    assert "libdsrt" not in loaded
