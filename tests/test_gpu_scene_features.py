@@ -141,6 +141,38 @@ def test_spheres_identical_to_live_reference_kernel(dsrt, with_lights):
     assert (img.reshape(-1, 3).max(1) > 0).mean() > 0.02
 
 
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libref_gpu.so not present")
+def test_reference_gpuscene_with_spheres_through_the_legacy_upload(dsrt):
+    """What the `gpu_render_scene` shim does with a reference GPUScene that holds spheres (round 1 refused them):
+    triangles, materials and spheres are taken from the DEVICE arrays the reference's build_gpu_scene produced
+    (dsrt_scene_upload_legacy); the LCG frame is the reference kernel's, byte for byte.  And the device path
+    range-checks material ids with a kernel."""
+    import torch
+    tris, mats, sph = sphere_scene(dsrt, True)
+    lookfrom = np.array((350, 260, 1500), np.float32)
+    cam = camera_at(dsrt, lookfrom)
+    ref = refgpu.RefScene(tris, mats, lookfrom, SUN, W, H, SPP, DEPTH, spheres=sph)
+    rimg, _ = ref.render()
+    with dsrt.Context(0) as c:
+        st, masked = c.upload_scene_legacy(ref.legacy_scene_ptr(), False)
+        assert st.num_triangles == len(tris) and masked == 0
+        c.render(cam, SUN, dsrt.make_params(W, H, SPP, DEPTH, dsrt.RNG_REF_LCG))
+        img = c.readback_rgb8(SPP, 2.0)
+        assert np.array_equal(img, rimg), f"{(img != rimg).any(2).sum()} pixels differ from the reference kernel"
+        bad = tris.copy()
+        bad["material_id"][17] = len(mats) + 3
+        d_tris = torch.from_numpy(bad.view(np.uint8).copy()).cuda()
+        d_mats = torch.from_numpy(mats.view(np.uint8).copy()).cuda()
+        with pytest.raises(dsrt.DsrtError, match="material_id"):
+            c.upload_scene_device(d_tris.data_ptr(), len(bad), d_mats.data_ptr(), len(mats))
+        d_ok = torch.from_numpy(tris.view(np.uint8).copy()).cuda()
+        d_sph = torch.from_numpy(sph.view(np.uint8).copy()).cuda()
+        c.upload_scene_device(d_ok.data_ptr(), len(tris), d_mats.data_ptr(), len(mats), d_sph.data_ptr(), len(sph))
+        c.render(cam, SUN, dsrt.make_params(W, H, SPP, DEPTH, dsrt.RNG_REF_LCG))
+        assert np.array_equal(c.readback_rgb8(SPP, 2.0), rimg)
+    ref.close()
+
+
 def panel_obj(dsrt, tmp_path):
     """A textured scene that exercises tex2D: a wall of quads whose uvs run outside [0,1] (wrap),
     two textures of different sizes, an untextured floor, a metal and a glass block."""
