@@ -34,7 +34,8 @@
 // --max_depth --seed --obj <path> --obj_scale S --synthetic_tris N --diffuse_only --gpus G
 // --shard frame|sample --frames a:b --rng philox|lcg --no_png --stats_json <file>
 // --dump_accum (also writes <frame>.accum, the raw float accumulation buffer) --sync_frames
-// (one frame at a time per GPU, as round 1 did).
+// (one frame at a time per GPU, as round 1 did) --resume (keep the output directory and render
+// only the frames whose files are missing).
 #include "dsrt.h"
 
 #include <algorithm>
@@ -67,7 +68,7 @@ struct Options {
     std::string pose_file, out_dir = "output", stats_json, shard = "frame", rng = "philox";
     std::string obj_path = "../../iss_model/ISS_stationary.obj";      // main.cpp:239
     double obj_scale = 1.0;
-    bool upscale = false, png = true, diffuse_only = false, dump_accum = false, sync_frames = false;
+    bool upscale = false, png = true, diffuse_only = false, dump_accum = false, sync_frames = false, resume = false;
     bool obj_given = false;
     int width = 800, height = 450, spp = 1000, max_depth = 50;
     int synthetic_tris = -1, gpus = 1, frame_begin = 0, frame_end = -1;      // -1: no synthetic stand-in
@@ -91,6 +92,7 @@ void parse_args(int argc, char** argv, Options& o) {
         else if (const char* v = next("--obj")) { o.obj_path = v; o.obj_given = true; }
         else if (a == "--dump_accum") o.dump_accum = true;
         else if (a == "--sync_frames") o.sync_frames = true;
+        else if (a == "--resume") o.resume = true;
         else if (const char* v = next("--obj_scale")) o.obj_scale = std::atof(v);
         else if (a == "--diffuse_only") o.diffuse_only = true;
         else if (const char* v = next("--gpus")) o.gpus = std::atoi(v);
@@ -506,7 +508,9 @@ int main(int argc, char** argv) {
     using clk = std::chrono::high_resolution_clock;
     Options o;
     parse_args(argc, argv, o);
-    prepare_output_dir(o.out_dir);
+    // --resume: frames are independent, so a sequence that was interrupted continues with the frames whose files are
+    // missing; the output directory is then NOT emptied (the reference always empties it, main.cpp:41-50)
+    if (o.resume) fs::create_directories(o.out_dir); else prepare_output_dir(o.out_dir);
 
     std::cout << "Using input_txt : " << (o.pose_file.empty() ? "(none)" : o.pose_file) << "\n";
     std::cout << "Using output_dir: " << o.out_dir << "\n";
@@ -597,6 +601,17 @@ int main(int argc, char** argv) {
             continue;
         }
         std::cout << "  sun_dir_model   = (" << j.sun_dir[0] << ", " << j.sun_dir[1] << ", " << j.sun_dir[2] << ")\n";
+        if (o.resume) {
+            char name[64];
+            std::snprintf(name, sizeof(name), "/frame_%04zu.ppm", j.index);
+            std::error_code ec;
+            const auto sz = fs::file_size(o.out_dir + name, ec);
+            std::snprintf(name, sizeof(name), "/frame_%04zu.png", j.index);
+            if (!ec && sz >= (uintmax_t)o.width * o.height * 3 && (!o.png || fs::exists(o.out_dir + name))) {
+                std::cout << "  already rendered (--resume)\n";
+                continue;
+            }
+        }
         jobs.push_back(j);
     }
 
@@ -625,7 +640,9 @@ int main(int argc, char** argv) {
         if (!keep.empty()) setenv("CUDA_VISIBLE_DEVICES", keep.c_str(), 1);
     }
     const auto render_start = clk::now();
-    if (o.shard == "sample" && G > 1) {
+    if (jobs.empty()) {
+        std::cout << "Nothing to render.\n";
+    } else if (o.shard == "sample" && G > 1) {
 #ifdef DSRT_WITH_NCCL
         rc = sample_sharded(o, scene, jobs, results, times);
 #else

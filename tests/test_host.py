@@ -272,3 +272,23 @@ def test_reference_arm_of_bench_does_not_map_the_product_library(tmp_path):
     loaded = "".join(f.read_text(errors="ignore") for f in tmp_path.glob("ld*"))
     assert "liboracle" in loaded or "libref_cpu" in loaded
     assert "libdsrt" not in loaded
+
+
+def test_cli_resume_skips_frames_that_exist(tmp_path):
+    """--resume keeps the output directory and renders only the frames whose files are missing; with every frame
+    present nothing is left to do and no device is needed."""
+    import subprocess
+    exe = ROOT / "deep-space-ray-tracer_b200" / "ray_tracer"
+    if not exe.exists():
+        pytest.skip("ray_tracer not built")
+    out = tmp_path / "frames"
+    out.mkdir()
+    for k in range(3):
+        (out / f"frame_{k:04d}.ppm").write_bytes(b"P6\n64 36\n255\n" + bytes(64 * 36 * 3))
+        (out / f"frame_{k:04d}.png").write_bytes(b"x")
+    (out / "keep.txt").write_text("not wiped")
+    r = subprocess.run([str(exe), "--input_txt", str(POSE_FILE), "--output_dir", str(out), "--synthetic_tris", "500", "--frames", "0:3",
+                        "--width", "64", "--height", "36", "--spp", "2", "--max_depth", "3", "--resume"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("already rendered (--resume)") == 3 and "Nothing to render." in r.stdout
+    assert (out / "keep.txt").exists() and (out / "frame_0001.png").read_bytes() == b"x"
