@@ -1017,16 +1017,13 @@ extern "C" int dsrt_reduce_accum(dsrt_ctx* ctx, void* nccl_comm, int root) {
     FrameSlot& f = ctx->slots[0];
     if (!f.accum) return fail(ctx, DSRT_EINVAL, "nothing rendered yet");
     typedef int (*reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
-    static reduce_fn fn = nullptr;
-    if (!fn) {
+    // looked up once, whichever of the per-GPU worker threads gets here first (C++11 static initialisation is thread-safe)
+    static const reduce_fn fn = [] {
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (h) fn = reinterpret_cast<reduce_fn>(dlsym(h, "ncclReduce"));
-        if (!fn) {
-            const char* why = dlerror();
-            return fail(ctx, DSRT_EUNSUPPORTED, "dsrt_reduce_accum: libnccl not found (%s)", why ? why : "no ncclReduce symbol");
-        }
-    }
+        return h ? reinterpret_cast<reduce_fn>(dlsym(h, "ncclReduce")) : (reduce_fn) nullptr;
+    }();
+    if (!fn) return fail(ctx, DSRT_EUNSUPPORTED, "dsrt_reduce_accum: libnccl.so.2 with ncclReduce not found");
     CK(cudaSetDevice(ctx->device));
     const size_t nf = (size_t)f.W * f.H * 3;
     const int rc = fn(f.accum, f.accum, nf, /*ncclFloat*/ 7, /*ncclSum*/ 0, root, nccl_comm, ctx->stream);
