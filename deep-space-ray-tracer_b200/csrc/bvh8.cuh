@@ -62,6 +62,9 @@ constexpr int kLocalStack = 40;        // overflow entries per thread in local m
                                        // Measured on B200 (profiles/r02_ab_variants.txt), C2 traversal ms: drain 8.71, n = 1: 8.84,
                                        // n = 2: 8.12, n = 3: 8.58; C5: 46.2 / 45.5 / 43.1 / 45.5
 #endif
+#ifndef DSRT_TRI_ROUND_MIN
+#define DSRT_TRI_ROUND_MIN 0           // k > 0 (with DSRT_TRI_PER_STEP = n): the warp runs a first round of one test per lane
+#endif                                 // and further rounds (up to n) only while at least k lanes still have a triangle pending
 #ifndef DSRT_PREFETCH_NEXT
 #define DSRT_PREFETCH_NEXT 0           // 1: visit() prefetches the node of the next visit into L1 (see there)
 #endif
@@ -394,6 +397,29 @@ struct LaneTravT {
         }
         if (tpend.y != 0u) return false;          // the rest of this node's triangles: next call
         return settle(stack, false);
+    }
+
+    // step_bounded() in pieces, for trace loops that decide per WARP how many rounds of triangle tests a step gets
+    // (DSRT_TRI_ROUND_MIN): the node visit of a lane with nothing pending, and one triangle test of a lane with something.
+    __device__ __forceinline__ void visit_pending(const uint4* __restrict__ nodes, TravStack& stack) {
+        uint32_t cur_node;
+        tpend = visit(nodes, stack, cur_node);
+        if (TRACK) tnode = cur_node;
+    }
+    // Tests the first pending triangle; true when an any-hit ray found its occluder.
+    __device__ __forceinline__ bool test_one(const float4* __restrict__ tris) {
+        const uint32_t bit = 31u - __clz(tpend.y);
+        tpend.y &= ~(1u << bit);
+        const uint32_t ti = tpend.x + bit;
+        float4 ra, rb, rc;
+        load_tri_record(tris + (size_t)ti * kTriWords, ra, rb, rc);
+        float t, u, v;
+        if (tri_test(ra, rb, rc, v3(ox, oy, oz), v3(dx, dy, dz), tmin, tmax, t, u, v)) {
+            tmax = t; hu = u; hv = v; htri = (int)ti;
+            if (TRACK) hnode = tnode;
+            if (any_hit) return true;
+        }
+        return false;
     }
 
     // ---- step() in three parts, for the trace loops that test triangles warp-cooperatively (pooled_tri_test) ----
