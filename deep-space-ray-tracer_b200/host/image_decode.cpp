@@ -9,8 +9,11 @@
 //   PNM   binary P5 / P6, maxval <= 65535 (16-bit -> high byte)
 //   BMP   uncompressed 8-bit paletted / 24-bit / 32-bit, bottom-up or top-down
 //   TGA   true-colour and grey, raw or RLE (types 2, 3, 10, 11), 8/24/32 bits
-// Anything else (JPEG, GIF, PSD, HDR ...) is reported as undecodable and the loader falls back
-// to the reference's own failure path, a 1x1 white texture (gpu_scene_builder.cpp:215-221).
+//   JPEG  baseline and progressive Huffman DCT, grey or YCbCr/RGB (jpeg_decode.cpp: stb_image's
+//         integer arithmetic restated, so the bytes are the reference's)
+// Anything else (GIF, PSD, HDR, CMYK or arithmetic-coded JPEG ...) is reported as undecodable; the
+// loader then takes the reference's own failure path, a 1x1 white texture
+// (gpu_scene_builder.cpp:215-221), and counts the file so that the CLI can refuse to render.
 #include "image_decode.h"
 
 #include <zlib.h>
@@ -303,6 +306,7 @@ bool decode_image_file(const char* path, DecodedImage& out, bool* exists) {
     if (exists) *exists = true;
     if (f.size() < 4) return false;
     if (f[0] == 0x89 && f[1] == 'P') return decode_png(f, out);
+    if (f[0] == 0xFF && f[1] == 0xD8) return decode_jpeg(f, out);
     if (f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return decode_pnm(f, out);
     if (f[0] == 'B' && f[1] == 'M') return decode_bmp(f, out);
     const size_t L = std::strlen(path);

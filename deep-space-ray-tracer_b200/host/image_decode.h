@@ -12,7 +12,10 @@ struct DecodedImage {
     std::vector<unsigned char> rgb;      // w*h*3, top row first
 };
 
-// Decodes PNG / binary PNM / BMP / TGA into 8-bit RGB.  false = unreadable or unsupported; *exists (may be NULL)
+// jpeg_decode.cpp
+bool decode_jpeg(const std::vector<unsigned char>& file, DecodedImage& out);
+
+// Decodes PNG / JPEG / binary PNM / BMP / TGA into 8-bit RGB.  false = unreadable or unsupported; *exists (may be NULL)
 // tells the two apart: the file could be read but is not an image this decoder understands.
 bool decode_image_file(const char* path, DecodedImage& out, bool* exists = nullptr);
 

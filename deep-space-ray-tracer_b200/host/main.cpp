@@ -542,10 +542,10 @@ int main(int argc, char** argv) {
                          std::to_string(v.num_textures) + " textures from " + o.obj_path;
             if (v.skipped_faces) scene_desc += " (" + std::to_string(v.skipped_faces) + " triangles with bad indices dropped)";
             if (v.textures_unsupported) {
-                // the reference decodes map_Kd files with stb_image (JPEG, GIF, PSD ... as well); a texture that exists
+                // the reference decodes map_Kd files with stb_image (GIF, PSD, HDR ... as well); a texture that exists
                 // but that this loader cannot decode would silently change the picture, so it is an error, not a white
                 // stand-in (a MISSING file is white in the reference too)
-                std::fprintf(stderr, "%d texture file(s) of %s exist but could not be decoded (supported: PNG, PNM, BMP, TGA); "
+                std::fprintf(stderr, "%d texture file(s) of %s exist but could not be decoded (supported: PNG, JPEG, PNM, BMP, TGA); "
                                      "convert them, or set DSRT_ALLOW_MISSING_TEXTURES=1 to render them white\n",
                              v.textures_unsupported, o.obj_path.c_str());
                 if (!std::getenv("DSRT_ALLOW_MISSING_TEXTURES")) { dsrt_mesh_free(mesh); return 1; }

@@ -232,8 +232,9 @@ int dsrt_synth_mesh(int ntris, uint32_t seed, int diffuse_only,
  * triangle_mesh's constructor argument does.  Returns DSRT_EIO when the OBJ cannot be opened
  * (the reference silently continues with an empty mesh), DSRT_ENOMEM / DSRT_EIO when the file is
  * too large or malformed (no exception crosses this boundary).  Texture files are decoded
- * in-process (PNG, binary PNM, BMP, TGA); a missing or undecodable file becomes a 1x1 white
- * texture, the reference's own failure path, and is counted in the view. */
+ * in-process (PNG, JPEG -- baseline and progressive, with stb_image's integer arithmetic, so the
+ * texels are the reference's --, binary PNM, BMP, TGA); a missing or undecodable file becomes a
+ * 1x1 white texture, the reference's own failure path, and is counted in the view. */
 typedef struct dsrt_mesh dsrt_mesh;
 typedef struct DsrtMeshView {
     const DsrtTriangle*      triangles;      int32_t num_triangles;
@@ -245,7 +246,7 @@ typedef struct DsrtMeshView {
     int32_t textures_failed;                 /* textures replaced by 1x1 white */
     int32_t textures_flipped;                /* 1 = pool rows are bottom-up (inc/texture.h:133 side effect) */
     int32_t textures_unsupported;            /* of textures_failed: the file exists but is in a format this loader does
-                                                not decode (the reference's stb_image also reads JPEG, GIF, PSD, HDR):
+                                                not decode (the reference's stb_image also reads GIF, PSD, HDR, PIC):
                                                 the picture WOULD differ from the reference's; the CLI refuses to render */
 } DsrtMeshView;
 int  dsrt_mesh_load_obj(const char* obj_path, double scale, dsrt_mesh** out);
