@@ -173,13 +173,21 @@ def test_reference_gpuscene_with_spheres_through_the_legacy_upload(dsrt):
     ref.close()
 
 
-def panel_obj(dsrt, tmp_path):
+def panel_obj(dsrt, tmp_path, jpeg=False):
     """A textured scene that exercises tex2D: a wall of quads whose uvs run outside [0,1] (wrap),
-    two textures of different sizes, an untextured floor, a metal and a glass block."""
+    two textures of different sizes, an untextured floor, a metal and a glass block.  jpeg: the two
+    textures are JPEG files (baseline 4:2:0 and progressive 4:4:4), which the reference decodes with stb_image."""
     rng = np.random.default_rng(5)
-    dsrt.write_ppm(tmp_path / "a.ppm", rng.integers(0, 256, (16, 24, 3)).astype(np.uint8), 24, 16)
-    dsrt.write_png(tmp_path / "b.png", rng.integers(0, 256, (9, 7, 3)).astype(np.uint8), 7, 9)
-    (tmp_path / "p.mtl").write_text("newmtl ta\nmap_Kd a.ppm\nnewmtl tb\nKd 0.2 0.2 0.2\nmap_Kd b.png\nnewmtl floor\nKd 0.6 0.6 0.55\n"
+    ta, tb = rng.integers(0, 256, (16, 24, 3)).astype(np.uint8), rng.integers(0, 256, (9, 7, 3)).astype(np.uint8)
+    na, nb = ("a.jpg", "b.jpg") if jpeg else ("a.ppm", "b.png")
+    if jpeg:
+        from PIL import Image
+        Image.fromarray(np.repeat(np.repeat(ta, 3, 0), 3, 1)).save(tmp_path / na, quality=88, subsampling=2)
+        Image.fromarray(np.repeat(np.repeat(tb, 4, 0), 4, 1)).save(tmp_path / nb, quality=92, subsampling=0, progressive=True)
+    else:
+        dsrt.write_ppm(tmp_path / na, ta, 24, 16)
+        dsrt.write_png(tmp_path / nb, tb, 7, 9)
+    (tmp_path / "p.mtl").write_text(f"newmtl ta\nmap_Kd {na}\nnewmtl tb\nKd 0.2 0.2 0.2\nmap_Kd {nb}\nnewmtl floor\nKd 0.6 0.6 0.55\n"
                                     "newmtl steel\nKs 0.8 0.8 0.85\nNs 400\nnewmtl glass\nd 0.3\nNi 1.5\n")
     L = ["mtllib p.mtl"]
     nv = 0
@@ -226,12 +234,12 @@ def test_textured_obj_vs_oracle(dsrt, tmp_path):
 
 
 @pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libref_gpu.so not present")
-@pytest.mark.parametrize("scene", ["panel", "station"])
+@pytest.mark.parametrize("scene", ["panel", "panel_jpeg", "station"])
 def test_obj_scene_identical_to_live_reference_kernel(dsrt, tmp_path, scene):
     """The reference loads the OBJ with its own triangle_mesh + stb_image and renders with its own
     kernel; this path loads it with dsrt_mesh_load_obj and renders through the C ABI."""
-    if scene == "panel":
-        path, scale, lookfrom = panel_obj(dsrt, tmp_path), 1.0, np.array((25, 30, 170), np.float32)
+    if scene in ("panel", "panel_jpeg"):
+        path, scale, lookfrom = panel_obj(dsrt, tmp_path, jpeg=scene == "panel_jpeg"), 1.0, np.array((25, 30, 170), np.float32)
     else:
         path, scale, lookfrom = OBJ_DIR / "station.obj", 2.5, np.array((3, 4, 22), np.float32)
     sun = np.array([-0.3, -0.5, -0.8], np.float32)
