@@ -292,3 +292,25 @@ def test_cli_resume_skips_frames_that_exist(tmp_path):
     assert r.returncode == 0, r.stderr
     assert r.stdout.count("already rendered (--resume)") == 3 and "Nothing to render." in r.stdout
     assert (out / "keep.txt").exists() and (out / "frame_0001.png").read_bytes() == b"x"
+
+
+def test_headers_are_plain_c_and_link_from_c(tmp_path):
+    """include/*.h compiled by a C99 compiler with -pedantic (no C++, no CUDA types), a C program linked against
+    libdsrt.so: record sizes, the host-side pose/camera entry points (Appendix B values) and, without a GPU, the loud
+    failure of dsrt_create."""
+    import subprocess
+    import torch
+    exe = tmp_path / "abi_check"
+    lib_dir = ROOT / "deep-space-ray-tracer_b200"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c" / "abi_check.c"),
+           "-o", str(exe), f"-L{lib_dir}", "-ldsrt", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(POSE_FILE)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sm_100a" in r.stdout and "poses 99 sep 1786.974223" in r.stdout
+    assert "cam -0.726112366 0 1786.97412 llc -1156.27637" in r.stdout          # SURVEY appendix B, frame 0
+    if torch.cuda.is_available():
+        assert "device ok" in r.stdout
+    else:
+        assert "no usable CUDA device" in r.stdout
