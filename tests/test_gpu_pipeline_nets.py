@@ -63,6 +63,8 @@ def assert_primary_hits(ours, ref, leaf, min_hits):
     assert hit.sum() >= min_hits, hit.sum()
     assert np.array_equal(bits(t)[hit], bits(rt)[hit])
     assert np.array_equal(bits(u)[hit], bits(ru)[hit]) and np.array_equal(bits(v)[hit], bits(rv)[hit])
+    if leaf is None:
+        return
     # the BVH leaf: the reported node has a leaf slot whose record range holds the reported record,
     # and that record is the reported triangle
     first, last, is_leaf, rec_tri = leaf
@@ -119,6 +121,41 @@ def test_config2_size_first_hits_of_the_primary_kernel(dsrt, poses, mesh1m):
             ours = c.primary_hits(cam, dsrt.make_params(w, h, spp, DEPTH, mode), sample=s)
             ref = sc.primary_hits(cam12_of(cam), w, h, spp, sample=s, rng_mode=omode)
             assert_primary_hits(ours, ref, leaf, 150000)
+
+
+def test_config5_size_10m_triangles(dsrt, poses):
+    """BASELINE config 5 geometry (10M triangles, diffuse only, 1920x1080, depth 16, pose 0), the scene that does not
+    fit L2: first hits of the production kernel bit-exact against the oracle for every pixel, 50 000 incoherent rays
+    bit-exact, any-hit == "a closest hit exists", exact ray conservation and determinism of a 4-spp frame."""
+    from gpu_probe import random_rays
+    tris, mats = dsrt.synth_mesh(10_000_000, diffuse_only=True)
+    w, h, spp, depth = 1920, 1080, 256, 16
+    cam_pos, sun, _ = dsrt.pose_to_model_frame(poses[0])
+    cam = dsrt.camera_look_at_origin(cam_pos, 40.0, w, h, spp, depth)
+    sc = oracle.Scene(tris, mats)
+    with dsrt.Context(0) as c:
+        st = c.upload_scene(tris, mats)
+        assert st.num_triangles == 10_000_000 and st.num_wide_nodes > 500_000
+        ours = c.primary_hits(cam, dsrt.make_params(w, h, spp, depth, dsrt.RNG_PHILOX), sample=101)
+        ref = sc.primary_hits(cam12_of(cam), w, h, spp, sample=101, rng_mode=0)
+        assert_primary_hits(ours, ref, None, 150000)
+        rays = random_rays(50000, 13, np.array(st.scene_lo[:]), np.array(st.scene_hi[:]))
+        tri, t, u, v = c.trace_closest(rays)
+        rtri, rt, ru, rv = sc.trace(rays)
+        same = tri == rtri
+        tie = (~same) & (tri >= 0) & (rtri >= 0) & (bits(t) == bits(rt))
+        assert (same | tie).all() and (same & (rtri >= 0)).sum() > 20000
+        hit = same & (rtri >= 0)
+        assert np.array_equal(bits(t)[hit], bits(rt)[hit]) and np.array_equal(bits(u)[hit], bits(ru)[hit])
+        assert np.array_equal(c.trace_occluded(rays).astype(bool), tri >= 0)
+        p4 = dsrt.make_params(w, h, 4, depth)
+        fs = c.render(cam, sun, p4)
+        a = c.readback_accum()
+        assert fs.primary_rays == w * h * 4 == fs.paths and fs.bounce_rays > 0 and fs.shadow_rays <= fs.bounce_rays + fs.primary_rays
+        assert 0 <= a.min() and a.max() <= 4
+        fs2 = c.render(cam, sun, p4)
+        assert fs2.rays == fs.rays and np.array_equal(c.readback_accum(), a)
+    sc.close()
 
 
 @pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libref_gpu.so not present")
