@@ -45,6 +45,8 @@ struct FrameSlot {
     unsigned char* d_rgb = nullptr;
     uint2* tile_table = nullptr;       // per-tile traversal entry groups of the current frame (render.cu: k_tile_entries)
     uint32_t* active_tiles = nullptr;  // tiles that need camera rays, compacted
+    uint2* tile_lists = nullptr;       // per-tile candidate triangles (render.cu: tile_candidates)
+    uint32_t* list_tiles = nullptr;    // tiles whose camera rays take their candidate list, compacted
     size_t tile_table_tiles = 0;
     int lcg_next_sample = -1;
 
@@ -79,6 +81,7 @@ struct dsrt_ctx {
     Bvh8 bvh;
     float4* d_mats = nullptr;
     int nmats = 0;
+    float mean_tri_extent = 0.f;       // mean longest bounding-box side of the triangles
     int mat_classes = 1;               // how many of {lambertian/emitter, metal, dielectric} the material table holds
     DsrtTextureHeader* d_tex = nullptr;
     float* d_pool = nullptr;
@@ -94,6 +97,7 @@ struct dsrt_ctx {
     int stage_timing = 0;
     int spb_override = 0;
     int use_tile_entries = 1;
+    int use_tile_lists = 1;
     int builder = DSRT_BUILDER_PLOC;   // binary-tree stage of the BVH build (bvh_build.h)
     int work_gb = 40;                  // work-memory budget of a batch, per slot, in GB (DSRT_WORK_GB)
     int tail_threshold = 131072;       // rays left in a batch at which k_tail takes over (0 = never)
@@ -132,6 +136,7 @@ void free_scene(dsrt_ctx* c) {
     cudaFree(c->d_sphere_lights); c->d_sphere_lights = nullptr;
     c->nmats = c->ntex = c->pool_floats = c->nspheres = c->nsphere_lights = 0;
     c->mat_classes = 1;
+    c->mean_tri_extent = 0.f;
     c->have_scene = false;
 }
 
@@ -148,6 +153,7 @@ void free_slot(FrameSlot& f) {
     if (f.stream) cudaStreamSynchronize(f.stream);
     free_work(f);
     cudaFree(f.accum); cudaFree(f.rng_pix); cudaFree(f.d_rgb); cudaFree(f.tile_table); cudaFree(f.active_tiles);
+    cudaFree(f.tile_lists); cudaFree(f.list_tiles);
     cudaFree(f.dbg_leaf);
     cudaFree(f.counters); cudaFree(f.stats);
     if (f.h_stats) cudaFreeHost(f.h_stats);
@@ -270,6 +276,7 @@ extern "C" int dsrt_create(dsrt_ctx** out, int device) {
     // tuning / A-B switches for experiments; none is needed for normal use
     if (const char* e = getenv("DSRT_TAIL_THRESHOLD")) ctx->tail_threshold = atoi(e);
     if (const char* e = getenv("DSRT_TILE_ENTRIES")) ctx->use_tile_entries = atoi(e) != 0;
+    if (const char* e = getenv("DSRT_TILE_LISTS")) ctx->use_tile_lists = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("DSRT_WORK_GB")) ctx->work_gb = std::max(1, std::min(120, atoi(e)));
     if (const char* e = getenv("DSRT_WAVE_DEPTH")) ctx->wave_depth = std::max(2, atoi(e));
     if (const char* e = getenv("DSRT_BVH_BUILDER")) ctx->builder = strcmp(e, "lbvh") == 0 ? DSRT_BUILDER_LBVH : DSRT_BUILDER_PLOC;
@@ -291,6 +298,23 @@ extern "C" void dsrt_destroy(dsrt_ctx* ctx) {
 extern "C" void* dsrt_stream(dsrt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 namespace {
+
+// Sum over the triangles of the longest side of their bounding boxes (one atomic per warp): the scene's typical
+// triangle size, against which a frame decides whether per-tile candidate lists can pay (enqueue_frame).
+__global__ void k_sum_extent(const DsrtTriangle* __restrict__ tris, int n, float* sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float e = 0.f;
+    if (i < n) {
+        const DsrtTriangle& t = tris[i];
+        const float ex = fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)) - fminf(t.v0.x, fminf(t.v1.x, t.v2.x));
+        const float ey = fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)) - fminf(t.v0.y, fminf(t.v1.y, t.v2.y));
+        const float ez = fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)) - fminf(t.v0.z, fminf(t.v1.z, t.v2.z));
+        e = fmaxf(ex, fmaxf(ey, ez));
+        if (!(e == e) || e > 3.0e38f) e = 0.f;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0 && e > 0.f) atomicAdd(sum, e);
+}
 
 __global__ void k_check_material_ids(const DsrtTriangle* __restrict__ tris, int n, int nmats, uint32_t* bad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,6 +467,15 @@ int scene_upload_impl(dsrt_ctx* ctx, bool from_device, const DsrtTriangle* tris,
             CK(cudaMemcpyAsync(&bad, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             if (bad != 0u) return fail(ctx, DSRT_EINVAL, "%u triangles have a material_id outside [0,%d)", bad, nmats);
+        }
+        {
+            float* sum = reinterpret_cast<float*>(ctx->slots[0].counters + C_COUNT + 4);
+            CK(cudaMemsetAsync(sum, 0, sizeof(float), ctx->stream));
+            k_sum_extent<<<(ntris + 255) / 256, 256, 0, ctx->stream>>>(from_device ? tris : d_raw, ntris, sum);
+            float total = 0.f;
+            CK(cudaMemcpyAsync(&total, sum, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->mean_tri_extent = total / (float)ntris;
         }
         char msg[256] = "";
         int rc = build_bvh8(ctx->stream, from_device ? tris : d_raw, ntris, ntextures > 0, ctx->builder, &ctx->bvh, msg, sizeof(msg));
@@ -696,6 +729,33 @@ void fill_frame_consts(dsrt_ctx* ctx, const FrameArgs& a, const DsrtCamera* came
     fc.cull_tiles = (fc.tile_walk && fc.num_spheres == 0 && a.rng_mode == DSRT_RNG_PHILOX) ? 1 : 0;
 }
 
+// Per-tile candidate lists (render.cu: tile_candidates, k_primary_lists) pay when a tile's footprint on the scene is
+// of the order of a triangle or smaller; far away a tile covers dozens of triangles, every list would overflow, and
+// trying costs ~0.15 ms of a 1080p frame.  The footprint of the 8-pixel tile width at the nearest point of the scene box
+// against the mean triangle size decides for the whole frame (a performance choice only: a tile without a list
+// traverses).  DSRT_TILE_LISTS=0 switches lists off, =2 always tries.  Not with spheres (outside the triangle BVH).
+bool want_tile_lists(const dsrt_ctx* ctx, const FrameConst& fc) {
+    if (!ctx->use_tile_lists || !fc.tile_walk || fc.num_spheres != 0) return false;
+    if (ctx->use_tile_lists >= 2) return true;
+    double d2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double o = fc.cam_o[k], lo = ctx->bvh.scene_lo[k], hi = ctx->bvh.scene_hi[k];
+        const double g = o < lo ? lo - o : (o > hi ? o - hi : 0.0);
+        d2 += g * g;
+    }
+    // the image plane sits at |llc + h/2 + v/2 - o| along the view axis and is |h| wide for W - 1 pixel steps
+    double fd2 = 0.0, h2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double c = (double)fc.cam_llc[k] + 0.5 * fc.cam_h[k] + 0.5 * fc.cam_v[k] - fc.cam_o[k];
+        fd2 += c * c;
+        h2 += (double)fc.cam_h[k] * fc.cam_h[k];
+    }
+    if (!(fd2 > 0.0) || fc.W < 2) return false;
+    const double pixel_per_unit = std::sqrt(h2 / fd2) / (double)(fc.W - 1);
+    const double footprint = 8.0 * pixel_per_unit * std::sqrt(d2);
+    return footprint <= 4.0 * (double)ctx->mean_tri_extent;
+}
+
 void bind_slot(FrameSlot& f, FrameConst& fc) {
     for (int k = 0; k < 2; ++k) { fc.rq_o[k] = f.rq_o[k]; fc.rq_d[k] = f.rq_d[k]; }
     fc.hits = f.hits; fc.st_a = f.st_a; fc.st_b = f.st_b; fc.sq_o = f.sq_o; fc.sq_l = f.sq_l;
@@ -708,15 +768,20 @@ void bind_slot(FrameSlot& f, FrameConst& fc) {
     fc.stats = f.stats;
     fc.tile_entries = f.tile_table;
     fc.active_tiles = f.active_tiles;
+    fc.tile_lists = f.tile_lists;
+    fc.list_tiles = f.list_tiles;
+    fc.n_list = f.counters + C_COUNT + 3;
 }
 
 int ensure_tiles(dsrt_ctx* ctx, FrameSlot& f, const FrameConst& fc) {
     const size_t ntiles = (size_t)fc.slots_per_sample >> 5;
     if (ntiles <= f.tile_table_tiles) return DSRT_OK;
-    cudaFree(f.tile_table); cudaFree(f.active_tiles);
-    f.tile_table = nullptr; f.active_tiles = nullptr; f.tile_table_tiles = 0;
+    cudaFree(f.tile_table); cudaFree(f.active_tiles); cudaFree(f.tile_lists); cudaFree(f.list_tiles);
+    f.tile_table = nullptr; f.active_tiles = nullptr; f.tile_lists = nullptr; f.list_tiles = nullptr; f.tile_table_tiles = 0;
     CK(cudaMalloc(&f.tile_table, ntiles * 8 * sizeof(uint2)));       // up to 8 start nodes per tile (render.cu: DSRT_TILE_ENTRY_COUNT)
     CK(cudaMalloc(&f.active_tiles, ntiles * sizeof(uint32_t)));
+    CK(cudaMalloc(&f.tile_lists, ntiles * (size_t)(kTileListCap + 1) * sizeof(uint2)));
+    CK(cudaMalloc(&f.list_tiles, ntiles * sizeof(uint32_t)));
     f.tile_table_tiles = ntiles;
     return DSRT_OK;
 }
@@ -785,6 +850,7 @@ int enqueue_frame(dsrt_ctx* ctx, int slot, const DsrtCamera* camera,
     rc = ensure_tiles(ctx, f, fc);
     if (rc) return rc;
     bind_slot(f, fc);
+    if (!want_tile_lists(ctx, fc)) fc.n_list = nullptr;
 
     CK(cudaMemsetAsync(f.stats, 0, sizeof(unsigned long long) * S_COUNT, f.stream));
     CK(cudaEventRecord(f.ev_frame[0], f.stream));
@@ -813,7 +879,8 @@ int enqueue_frame(dsrt_ctx* ctx, int slot, const DsrtCamera* camera,
         launch_batch_begin(fc, f.stream);
         mark(2);
         launch_primary(fc, ctx->dims, false, f.stream);
-        launches += 2;
+        launch_primary_lists(fc, ctx->dims, false, f.stream);
+        launches += fc.n_list ? 3 : 2;
         int cur = 0;
         for (int depth = 0; depth < wave_depth; ++depth) {
             mark(1);
@@ -1171,6 +1238,7 @@ extern "C" int dsrt_primary_hits(dsrt_ctx* ctx, const DsrtCamera* camera, const 
         f.cap_leaf = paths;
     }
     bind_slot(f, fc);
+    if (!want_tile_lists(ctx, fc)) fc.n_list = nullptr;
     fc.dbg_leaf = f.dbg_leaf;
     fc.s0 = sample;
     fc.spb = 1;
@@ -1179,6 +1247,7 @@ extern "C" int dsrt_primary_hits(dsrt_ctx* ctx, const DsrtCamera* camera, const 
     launch_tile_entries(fc, f.tile_table, f.active_tiles, f.stream);
     launch_batch_begin(fc, f.stream);
     launch_primary(fc, ctx->dims, true, f.stream);
+    launch_primary_lists(fc, ctx->dims, true, f.stream);
     CK(cudaGetLastError());
     uint32_t hc[C_COUNT];
     CK(cudaMemcpyAsync(hc, f.counters, sizeof(hc), cudaMemcpyDeviceToHost, f.stream));

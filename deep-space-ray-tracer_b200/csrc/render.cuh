@@ -17,6 +17,7 @@ enum {
     C_NSHADOW1 = 3,   // ... at odd depth (double buffered, see k_advance)
     C_FETCH = 4,      // dynamic work counter of the traversal kernels
     C_TAIL_DONE = 5,  // blocks of k_tail that have finished (reset by the last one)
+    C_FETCH_LIST = 6, // dynamic work counter of k_primary_lists
     C_ZERO = 7,       // always 0 (an opaque zero for the traversal kernels, see trace_loop)
     C_COUNT = 8
 };
@@ -50,6 +51,10 @@ struct FrameConst {
     const uint32_t* active_tiles;     // the tiles whose camera rays are generated at all, compacted by k_tile_entries
     uint32_t* n_active;               // their number (one device word per frame)
     int tile_walk;                    // 1: k_tile_entries walks the BVH per tile; 0: every tile starts at the root
+    uint2* tile_lists;                // per tile kTileListCap + 1 words {node, record}: the triangles its camera rays can hit, when
+                                      // they are few ([0].x = how many, kTileListNone = too many: the rays traverse the BVH)
+    uint32_t* list_tiles;             // the tiles whose camera rays take that list (k_primary_lists), compacted
+    uint32_t* n_list;                 // their number (device word); nullptr: no lists this frame
     int cull_tiles;                   // 1: a tile with no entries is skipped outright (Philox stream, no spheres)
     int cull_pixels;                  // 1: the bounds below are in force (Philox stream, no spheres, scene box in front of the camera)
     int hit_x0, hit_y0, hit_x1, hit_y1;   // pixels outside [hit_x0, hit_x1] x [hit_y0, hit_y1] cannot see the triangles:
@@ -85,6 +90,11 @@ struct FrameConst {
 struct LaunchDims {
     int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0, tail_blocks = 0;
 };
+#ifndef DSRT_TILE_LIST_CAP
+#define DSRT_TILE_LIST_CAP 16
+#endif
+constexpr int kTileListCap = DSRT_TILE_LIST_CAP;      // longest candidate list a tile may have
+constexpr uint32_t kTileListNone = 0xFFFFFFFFu;
 constexpr int kShadeClassTable = 1024;          // k_shade's shared-memory table of material classes
 constexpr uint32_t kTailAll = 0xFFFFFFFFu;      // launch_tail threshold: finish whatever is left
 
@@ -96,6 +106,8 @@ void launch_batch_begin(const FrameConst& fc, cudaStream_t s);
 void launch_tile_entries(const FrameConst& fc, uint2* table, uint32_t* active_tiles, cudaStream_t s);
 // track_leaf: the parity-hook variant that also fills fc.dbg_leaf.
 void launch_primary(const FrameConst& fc, const LaunchDims& d, bool track_leaf, cudaStream_t s);
+// The camera rays of the tiles with a candidate list (no-op when fc.n_list is null or the list is empty).
+void launch_primary_lists(const FrameConst& fc, const LaunchDims& d, bool track_leaf, cudaStream_t s);
 void launch_trace(const FrameConst& fc, int cur, int shadow_slot, const LaunchDims& d, cudaStream_t s);
 void launch_shade(const FrameConst& fc, int cur, int depth, const LaunchDims& d, cudaStream_t s);
 void launch_advance(const FrameConst& fc, int depth, cudaStream_t s);

@@ -274,7 +274,10 @@ def test_legacy_boundary_renders_geometry_like_the_reference_kernel(dsrt, tmp_pa
     ndiff = int((img != rimg).any(2).sum())
     print(f"{binary} / {scene}: {ndiff} of 360000 pixels differ from the reference kernel's frame")
     if scene == "station":
-        assert ndiff == 0
+        # byte-identical while every camera ray traversed the BVH; since tiles with few candidate triangles test a
+        # list instead (k_primary_lists), 1 pixel of this fixture takes the other side of an exact-t tie on a shared
+        # edge (test_tile_lists_agree_with_traversal shows that ties are the only difference between the two paths)
+        assert ndiff <= 4
     else:
         # 800x450x1000 = 3.6e8 camera rays plus as many bounce and shadow rays through a mesh whose triangles share
         # edges exactly: a handful of rays hit a shared edge at bit-equal t in two triangles, where the reference
@@ -476,3 +479,46 @@ def test_flat_box_quirk_measured_and_reproduced_through_the_legacy_scene(dsrt, t
     (out / "flatbox_quirk.log").write_text(
         f"panel model: {ntris} triangles, {masked} in zero-thickness reference leaves; {w}x{h} first hits: {differ} of "
         f"{int((tri >= 0).sum())} covered pixels differ without DSRT_REF_FLATBOX, 0 with it; triangles seen {seen_ref} (reference) vs {seen_here}\n")
+
+
+def test_tile_lists_agree_with_traversal(dsrt, poses, mesh10k):
+    """Close to the station the camera rays of a tile test a short list of candidate triangles (k_tile_entries ->
+    k_primary_lists) instead of traversing the BVH.  Same scene, same rays, lists on and off (DSRT_TILE_LISTS): the
+    first hits of 40 samples x every pixel may differ only where two triangles are hit at bit-equal t (the winner of
+    such a tie depends on the visiting order, in the reference as here), and most tiles really took the list."""
+    w, h, spp = 320, 180, 64
+    scenes = [("synthetic, pose 98", mesh10k, dsrt.pose_to_model_frame(poses[98])[0]),
+              ("synthetic, 12 m above a module", mesh10k, np.array((120.0, 40.0, 37.0), np.float32))]
+    st = dsrt.load_obj(OBJ_DIR / "station.obj", 2.5)
+    scenes.append(("station.obj fixture", (st["tris"], st["mats"]), np.array((3.0, 4.0, 22.0), np.float32)))
+    for name, (tris, mats), lookfrom in scenes:
+        cam = dsrt.camera_look_at_origin(lookfrom, 40.0, w, h, spp, DEPTH)
+        params = dsrt.make_params(w, h, spp, DEPTH, dsrt.RNG_PHILOX)
+        res = {}
+        for lists in ("2", "0"):                      # 2: always try lists, whatever the distance
+            os.environ["DSRT_TILE_LISTS"] = lists
+            try:
+                with dsrt.Context(0) as c:
+                    c.upload_scene(tris, mats)
+                    res[lists] = [c.primary_hits(cam, params, sample=s) for s in range(0, 40)]
+                    if lists == "2":
+                        fs = c.render(cam, np.array([0.3, -0.7, 0.5], np.float32), params)
+                        acc_on = c.readback_accum()
+                    else:
+                        c.render(cam, np.array([0.3, -0.7, 0.5], np.float32), params)
+                        acc_off = c.readback_accum()
+            finally:
+                del os.environ["DSRT_TILE_LISTS"]
+        ties = hits = 0
+        for a, b in zip(res["2"], res["0"]):
+            same = a[0] == b[0]
+            tie = (~same) & (a[0] >= 0) & (b[0] >= 0) & (bits(a[1]) == bits(b[1]))
+            assert (same | tie).all(), f"{name}: {(~(same | tie)).sum()} first hits differ between the list and the traversal"
+            ok = same & (a[0] >= 0)
+            assert np.array_equal(bits(a[1])[ok], bits(b[1])[ok]) and np.array_equal(bits(a[2])[ok], bits(b[2])[ok])
+            ties += int(tie.sum())
+            hits += int(ok.sum())
+        assert hits > 100000
+        # the frames agree except for paths that start on the other side of a tie
+        assert (np.abs(acc_on - acc_off).sum(2) > 0).sum() <= max(4, 4 * ties), name
+        print(f"{name}: {hits} first hits identical, {ties} exact-t ties resolved the other way")
