@@ -91,7 +91,7 @@ struct LaunchDims {
     int primary_blocks = 0, trace_blocks = 0, shade_blocks = 0, tail_blocks = 0;
 };
 #ifndef DSRT_TILE_LIST_CAP
-#define DSRT_TILE_LIST_CAP 16
+#define DSRT_TILE_LIST_CAP 64
 #endif
 constexpr int kTileListCap = DSRT_TILE_LIST_CAP;      // longest candidate list a tile may have
 constexpr uint32_t kTileListNone = 0xFFFFFFFFu;

@@ -15,11 +15,23 @@ def frames_of_rank(num_frames: int, rank: int, world: int) -> list[int]:
     return list(range(rank, num_frames, world))
 
 
+# Device time (ms) of one frame of the shipped approach sequence at seven camera distances (m), 1080p, 250 spp, depth 50,
+# 1M triangles (profiles/r02_pose_split.txt, final code); only the ratios matter.
+_COST_TABLE = ((35.7, 304.0), (71.5, 147.0), (143.0, 78.0), (268.0, 81.5), (536.1, 50.0), (1072.2, 54.0), (1787.0, 37.0))
+
+
 def frame_cost(sep_m: float) -> float:
-    """Relative cost of one frame of the shipped kind of sequence: a floor plus the share of the image the station
-    covers, which grows as the camera closes in and saturates when the station fills the frame (fitted to per-frame
-    device times of the 99-pose sequence at 1080p; only the ratios matter)."""
-    return 60.0 + 190.0 * min(1.0, (300.0 / max(sep_m, 1e-9)) ** 2)
+    """Relative cost of one frame of the shipped kind of sequence: the measured per-frame device times, interpolated
+    in log(distance) -- flat while the station is a small part of the image, about twice that once it fills it, then
+    growing like 1/distance as the camera moves into the structure and every path bounces more often."""
+    import math
+    t = _COST_TABLE
+    x = math.log(min(max(sep_m, t[0][0]), t[-1][0]))
+    for (s0, c0), (s1, c1) in zip(t, t[1:]):
+        if x <= math.log(s1):
+            w = (x - math.log(s0)) / (math.log(s1) - math.log(s0))
+            return c0 + w * (c1 - c0)
+    return t[-1][1]
 
 
 def lpt_assignment(costs: list[float], world: int) -> list[list[int]]:

@@ -9,6 +9,7 @@ for v in main $VARS; do
   echo "== $v"
   DSRT_LIB=$LIB timeout 300 python tests/gpu_pose_split.py 2>&1 | tee gpurun_out/pose_split_${TAG}_$v.txt
 done
+[ -n "$NO_NCU" ] && exit 0
 CMD="python tests/gpu_pose_frame.py 98 64 10"
 $CMD && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_pose98_$TAG.csv $CMD > gpurun_out/ncu_pose98_$TAG.log 2>&1
 echo ncu_rc=$?
