@@ -65,12 +65,6 @@ constexpr int kLocalStack = 40;        // overflow entries per thread in local m
 #ifndef DSRT_TRI_ROUND_MIN
 #define DSRT_TRI_ROUND_MIN 0           // k > 0 (with DSRT_TRI_PER_STEP = n): the warp runs a first round of one test per lane
 #endif                                 // and further rounds (up to n) only while at least k lanes still have a triangle pending
-#ifndef DSRT_BANK
-#define DSRT_BANK 0                    // 1: step_banked -- a lane keeps visiting nodes while the triangles of up to two visits wait,
-#endif                                 // and the warp tests triangles only every DSRT_TRI_PERIOD-th step (DSRT_TRI_PER_STEP each)
-#ifndef DSRT_TRI_PERIOD
-#define DSRT_TRI_PERIOD 2
-#endif
 #ifndef DSRT_PREFETCH_NEXT
 #define DSRT_PREFETCH_NEXT 0           // 1: visit() prefetches the node of the next visit into L1 (see there)
 #endif
@@ -291,10 +285,6 @@ struct LaneTravT {
     uint32_t hnode;               // TRACK only: the node visited when htri was accepted
     uint32_t tnode;               // TRACK only: the node whose triangles are pending in tpend
     uint2 tpend;                  // DSRT_TRI_PER_STEP > 0: triangles of the last node visit that still wait for their test
-#if DSRT_BANK
-    uint2 tpend2;                 // step_banked: the triangles of the visit after that one
-    uint32_t tnode2;              // TRACK only
-#endif
     uint32_t octinv;
     uint2 ngroup;
     uint32_t one;                 // 0x3F800000 held in a register (see plane_byte)
@@ -312,9 +302,6 @@ struct LaneTravT {
         octinv = 7u - oct;
         ngroup = make_uint2(0u, 0x80000000u);      // the root as a one-bit node group
         tpend = make_uint2(0u, 0u);
-#if DSRT_BANK
-        tpend2 = make_uint2(0u, 0u);
-#endif
         any_hit = any_hit_;
         stack.sp = 0;
     }
@@ -331,9 +318,6 @@ struct LaneTravT {
         octinv = __float_as_uint(inv.w);
         ngroup = make_uint2(0u, 0x80000000u);
         tpend = make_uint2(0u, 0u);
-#if DSRT_BANK
-        tpend2 = make_uint2(0u, 0u);
-#endif
         any_hit = any_hit_;
         stack.sp = 0;
     }
@@ -414,52 +398,6 @@ struct LaneTravT {
         if (tpend.y != 0u) return false;          // the rest of this node's triangles: next call
         return settle(stack, false);
     }
-
-#if DSRT_BANK
-    // step_bounded() without the sit-out, and with the triangle tests of a warp gathered into fewer, wider rounds.  A lane
-    // keeps visiting nodes while the triangles of up to two visits wait in its bank (tpend, then tpend2); the warp runs a
-    // round of tests only when `tri_round` says so (warp-uniform: every DSRT_TRI_PERIOD-th step), each lane then testing at
-    // most `max_tests` of its banked triangles, oldest first.  Hits are those of step(): the tests happen in the same order
-    // against a shrinking closed interval; because a lane's t_max now shrinks a little later, it may visit boxes (and test
-    // triangles) that step() would have culled -- all of them behind the hit it is about to find, so none is accepted.
-    // A finished node walk is marked by ngroup = {0xFFFFFFFF, 0}.
-    __device__ __forceinline__ bool step_banked(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                TravStack& stack, bool tri_round, int max_tests) {
-        const bool walk_done = ngroup.y == 0u && ngroup.x == 0xFFFFFFFFu;
-        if (!walk_done && tpend2.y == 0u) {
-            uint32_t cur_node;
-            const uint2 g = visit(nodes, stack, cur_node);
-            if (tpend.y == 0u) { tpend = g; if (TRACK) tnode = cur_node; }
-            else { tpend2 = g; if (TRACK) tnode2 = cur_node; }
-            if (ngroup.y <= 0x00FFFFFFu) {
-                if (stack.sp == 0) ngroup = make_uint2(0xFFFFFFFFu, 0u);
-                else ngroup = stack.pop();
-            }
-        }
-        if (tri_round) {
-            const V3 orig = v3(ox, oy, oz), dir = v3(dx, dy, dz);
-            for (int k = 0; k < max_tests; ++k) {
-                if (tpend.y == 0u) {
-                    tpend = tpend2; tpend2.y = 0u;
-                    if (TRACK) tnode = tnode2;
-                    if (tpend.y == 0u) break;
-                }
-                const uint32_t bit = 31u - __clz(tpend.y);
-                tpend.y &= ~(1u << bit);
-                const uint32_t ti = tpend.x + bit;
-                float4 ra, rb, rc;
-                load_tri_record(tris + (size_t)ti * kTriWords, ra, rb, rc);
-                float t, u, v;
-                if (tri_test(ra, rb, rc, orig, dir, tmin, tmax, t, u, v)) {
-                    tmax = t; hu = u; hv = v; htri = (int)ti;
-                    if (TRACK) hnode = tnode;
-                    if (any_hit) return true;
-                }
-            }
-        }
-        return ngroup.y == 0u && ngroup.x == 0xFFFFFFFFu && tpend.y == 0u && tpend2.y == 0u;
-    }
-#endif
 
     // step_bounded() in pieces, for trace loops that decide per WARP how many rounds of triangle tests a step gets
     // (DSRT_TRI_ROUND_MIN): the node visit of a lane with nothing pending, and one triangle test of a lane with something.
